@@ -1,0 +1,184 @@
+// C-ABI entry points of the tap-GEMM family: they only describe the problem (extents, taps, tile
+// shape) and hand it to the tcgen05 kernel (or, for debugging, the SIMT cross-check kernel).
+#include "common.h"
+#include "tapgemm.h"
+
+namespace vg {
+
+static int g_tapgemm_impl = 0;  // 0 = sm100 (tcgen05), 1 = simt
+
+static int pick_bn(long n, int geglu) {
+  if (geglu) {
+    for (int bn = 256; bn >= 64; bn -= 64)
+      if (n % bn == 0) return bn;
+    return 0;
+  }
+  if (n <= 96) return (int)((n + 31) / 32) * 32;
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 96; bn -= 32) {
+    const long nb = (n + bn - 1) / bn;
+    const double cost = (double)nb * bn * (1.0 + 24.0 / bn);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+// choose the (box1, box2) output tile (<=128 positions) that wastes the fewest MMA rows
+static void pick_box(long d1, long d2, int* b1, int* b2) {
+  double best = -1;
+  int bb1 = 1, bb2 = 1;
+  const int max1 = (int)(d1 < 128 ? d1 : 128);
+  for (int x = max1; x >= 1; --x) {
+    int y = 128 / x;
+    if (y > d2) y = (int)d2;
+    if (y > 256) y = 256;
+    const double tiles = (double)cdiv(d1, x) * cdiv(d2, y);
+    const double eff = (double)d1 * d2 / (tiles * 128.0);
+    if (eff > best + 1e-9) {
+      best = eff;
+      bb1 = x;
+      bb2 = y;
+    }
+  }
+  *b1 = bb1;
+  *b2 = bb2;
+}
+
+static int fill_epilogue(TapGemmArgs* t, void* out, long ldo, const vgen_epilogue* epi) {
+  TapGemmEpilogue& e = t->epi;
+  e.out = reinterpret_cast<__half*>(out);
+  e.ldo = ldo;
+  e.alpha = epi ? epi->alpha : 1.0f;
+  e.bias = epi ? epi->bias : nullptr;
+  e.group_bias = epi ? reinterpret_cast<const __half*>(epi->group_bias) : nullptr;
+  e.ld_group_bias = epi ? epi->group_bias_ld : 0;
+  e.residual = epi ? reinterpret_cast<const __half*>(epi->residual) : nullptr;
+  e.ldr = epi ? epi->residual_ld : 0;
+  e.geglu = epi ? epi->geglu : 0;
+  return 0;
+}
+
+static int finish_and_launch(TapGemmArgs* t, const vgen_epilogue* epi, void* stream) {
+  TapGemmShape& s = t->shape;
+  s.kc = s.c / 64;
+  int bn = (epi && epi->bn > 0) ? epi->bn : pick_bn(s.n, t->epi.geglu);
+  VG_REQUIRE(bn > 0, "tapgemm: no valid N tile (GEGLU needs n % 64 == 0)");
+  s.bn = bn;
+  s.nb = cdiv(s.n, bn);
+  s.t1 = cdiv(s.d1, s.box1);
+  s.t2 = cdiv(s.d2, s.box2);
+  const long tiles = (long)s.d3 * s.t2 * s.t1 * s.nb;
+  VG_REQUIRE(tiles < (1L << 31), "tapgemm: too many tiles");
+  s.total_tiles = (int)tiles;
+  if (tiles == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_tapgemm_impl == 1 || (s.c % 64) != 0) return tapgemm_simt_launch(*t, st);
+  return tapgemm_sm100_launch(*t, st);
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" {
+
+int vgen_set_tapgemm_impl(int impl) {
+  if (impl != 0 && impl != 1) return fail("vgen_set_tapgemm_impl: impl must be 0 (sm100) or 1 (simt)");
+  g_tapgemm_impl = impl;
+  return 0;
+}
+
+int vgen_linear(const void* a, int64_t m, int64_t k, int64_t lda, const void* w, int64_t n, void* out, int64_t ldo,
+                const vgen_epilogue* epi, void* stream) {
+  VG_REQUIRE(a && w && out, "vgen_linear: null pointer");
+  VG_REQUIRE(m >= 0 && k > 0 && n > 0 && lda >= k, "vgen_linear: bad shape");
+  if (m == 0) return 0;
+  TapGemmArgs t{};
+  t.a = reinterpret_cast<const __half*>(a);
+  t.w = reinterpret_cast<const __half*>(w);
+  t.a_stride1 = lda;
+  t.a_stride2 = lda * m;
+  t.a_stride3 = lda * m;
+  TapGemmShape& s = t.shape;
+  s.c = (int)k;
+  s.d1 = (int)m;
+  s.d2 = 1;
+  s.d3 = 1;
+  s.box1 = 128;
+  s.box2 = 1;
+  s.num_taps = 1;
+  s.tap1[0] = s.tap2[0] = s.tap3[0] = 0;
+  s.n = (int)n;
+  fill_epilogue(&t, out, ldo, epi);
+  VG_REQUIRE(!t.epi.group_bias, "vgen_linear: group_bias is only defined for conv entries");
+  return finish_and_launch(&t, epi, stream);
+}
+
+int vgen_conv2d_3x3(const void* x, int64_t nimg, int64_t h, int64_t w_, int64_t c, const void* w, int64_t n, void* out,
+                    int64_t ldo, const vgen_epilogue* epi, void* stream) {
+  VG_REQUIRE(x && w && out, "vgen_conv2d_3x3: null pointer");
+  VG_REQUIRE(nimg >= 0 && h > 0 && w_ > 0 && c > 0 && n > 0, "vgen_conv2d_3x3: bad shape");
+  if (nimg == 0) return 0;
+  TapGemmArgs t{};
+  t.a = reinterpret_cast<const __half*>(x);
+  t.w = reinterpret_cast<const __half*>(w);
+  t.a_stride1 = c;
+  t.a_stride2 = c * w_;
+  t.a_stride3 = c * w_ * h;
+  TapGemmShape& s = t.shape;
+  s.c = (int)c;
+  s.d1 = (int)w_;
+  s.d2 = (int)h;
+  s.d3 = (int)nimg;
+  pick_box(w_, h, &s.box1, &s.box2);
+  s.num_taps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      s.tap1[ky * 3 + kx] = kx - 1;
+      s.tap2[ky * 3 + kx] = ky - 1;
+      s.tap3[ky * 3 + kx] = 0;
+    }
+  s.n = (int)n;
+  fill_epilogue(&t, out, ldo, epi);
+  return finish_and_launch(&t, epi, stream);
+}
+
+int vgen_tconv3(const void* x, int64_t f, int64_t hw, int64_t c, const void* w, int64_t n, void* out, int64_t ldo,
+                const vgen_epilogue* epi, void* stream) {
+  VG_REQUIRE(x && w && out, "vgen_tconv3: null pointer");
+  VG_REQUIRE(f >= 0 && hw > 0 && c > 0 && n > 0, "vgen_tconv3: bad shape");
+  if (f == 0) return 0;
+  TapGemmArgs t{};
+  t.a = reinterpret_cast<const __half*>(x);
+  t.w = reinterpret_cast<const __half*>(w);
+  t.a_stride1 = c;
+  t.a_stride2 = c * hw;
+  t.a_stride3 = c * hw * f;
+  TapGemmShape& s = t.shape;
+  s.c = (int)c;
+  s.d1 = (int)hw;
+  s.d2 = (int)f;
+  s.d3 = 1;
+  s.box1 = (int)(hw < 128 ? hw : 128);
+  s.box2 = 1;
+  if (hw < 128) {  // small planes: put several frames in one tile
+    s.box2 = (int)(128 / hw);
+    if (s.box2 > f) s.box2 = (int)f;
+  }
+  s.num_taps = 3;
+  for (int kt = 0; kt < 3; ++kt) {
+    s.tap1[kt] = 0;
+    s.tap2[kt] = kt - 1;
+    s.tap3[kt] = 0;
+  }
+  s.n = (int)n;
+  fill_epilogue(&t, out, ldo, epi);
+  VG_REQUIRE(!t.epi.group_bias, "vgen_tconv3: group_bias not supported");
+  return finish_and_launch(&t, epi, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// Host-side helpers shared by every translation unit of libvgen_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/vgen_b200.h"
+
+namespace vg {
+
+// Error plumbing: every C-ABI entry returns 0 on success, non-zero on failure, and the message is
+// kept per host thread for vgen_last_error().
+void set_error(const std::string& msg);
+int fail(const std::string& msg);
+int check_cuda(cudaError_t e, const char* what);
+
+#define VG_CUDA(expr)                                   \
+  do {                                                  \
+    int _rc = ::vg::check_cuda((expr), #expr);          \
+    if (_rc) return _rc;                                \
+  } while (0)
+#define VG_LAUNCH_CHECK(name)                                   \
+  do {                                                          \
+    ::vg::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+    int _rc = ::vg::check_cuda(cudaGetLastError(), name);       \
+    if (_rc) return _rc;                                        \
+  } while (0)
+#define VG_REQUIRE(cond, msg)                                          \
+  do {                                                                 \
+    if (!(cond)) return ::vg::fail(std::string(msg) + " [" #cond "]"); \
+  } while (0)
+
+// Encode a tiled, 128B-swizzled fp16 tensor map (rank <= 4). dims/box are innermost-first;
+// strides_bytes has rank-1 entries (dims 1..rank-1). Out-of-bounds elements read as zero.
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
+
+int sm_count();
+extern std::atomic<long long> g_launches;  // kernels launched by this library (vgen_launch_count)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace vg

@@ -1,0 +1,339 @@
+// tapgemm: the one tensor-core kernel behind every conv / linear of the UNet and the VAE.
+//
+//   out[row, n] = epilogue( sum_{tap} sum_{c} A[coord(row) + offset(tap), c] * W[n, tap*C + c] )
+//
+// A is an fp16 activation tensor in channels-last layout, viewed as a rank-4 box-tiled TMA tensor
+// {C, d1, d2, d3}.  A "tap" is a coordinate offset (e.g. the 9 taps of a 3x3 conv, the 3 taps of the
+// temporal (3,1,1) conv, or the single tap of a linear / 1x1 conv).  Out-of-range coordinates are
+// zero-filled by the TMA unit, which IS the conv's zero padding - there is no im2col buffer and no
+// halo handling in the kernel.  Per k-iteration the producer issues one 4-D box load of A
+// ([box2][box1][64 ch], 128B-swizzled, = the 128-row K-major UMMA A tile) and one 2-D load of W.
+//
+// Reference ops this replaces (all cuDNN / cuBLAS calls in the reference):
+//   nn.Conv2d 3x3 in ResBlock          /root/reference/tools/modules/unet/util.py:845-876
+//   nn.Conv3d (3,1,1) TemporalConvBlock_v2                                   util.py:1662-1680
+//   nn.Linear (q/k/v/out, GEGLU, FF, proj_in/out)                            util.py:224-229,707-741,338
+//   nn.Conv1d k=1 (TemporalTransformer proj)                                 util.py:1213,1229
+//   VAE conv3x3 / 1x1                  /root/reference/tools/modules/autoencoder.py:282-335,344-363
+//
+// Structure (sm_100a): persistent CTAs (one per SM), warp-specialised:
+//   warp 0      TMA producer (one elected lane), kStages-deep smem ring, mbarrier full/empty
+//   warp 1      tcgen05.mma issuer (one lane), fp32 accumulators in TMEM, double-buffered (2 x 256 cols)
+//   warps 2-5   epilogue: tcgen05.ld -> alpha / bias / per-frame bias / residual / GEGLU -> fp16 -> HBM
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.h"
+#include "ptx.cuh"
+#include "tapgemm.h"
+
+namespace vg {
+
+static constexpr int kBM = 128;       // rows per tile (UMMA M)
+static constexpr int kBK = 64;        // K per pipeline stage = one 128B swizzle row of fp16
+static constexpr int kThreads = 192;  // 6 warps
+static constexpr uint32_t kTmemCols = 512;
+static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+
+struct alignas(64) TapGemmKernelParams {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  TapGemmShape s;
+  TapGemmEpilogue e;
+  int stages;
+  int b_slot_bytes;  // smem bytes reserved per stage for the W tile (>= BN*128, multiple of 1024)
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid_constant__ TapGemmKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024B alignment is required by the 128B swizzle atom (8 rows x 128 B).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const int stage_bytes = kABytes + p.b_slot_bytes;
+
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* full_bar = bars;                 // [stages]
+  uint64_t* empty_bar = bars + stages;       // [stages]
+  uint64_t* tfull_bar = bars + 2 * stages;   // [2]
+  uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const TapGemmShape& s = p.s;
+  const int k_iters = s.num_taps * s.kc;
+  const int BN = s.bn;
+  const uint32_t stage_tx = (uint32_t)(s.box1 * s.box2 * kBK * 2 + BN * kBK * 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<kTmemCols>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it_g = 0;
+      for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x) {
+        int nb_i = tile % s.nb;
+        int rest = tile / s.nb;
+        const int t1_i = rest % s.t1;
+        rest /= s.t1;
+        const int t2_i = rest % s.t2;
+        const int i3 = rest / s.t2;
+        const int i1_0 = t1_i * s.box1, i2_0 = t2_i * s.box2, n0 = nb_i * BN;
+        for (int it = 0; it < k_iters; ++it, ++it_g) {
+          const int st = it_g % stages;
+          const uint32_t ph = (it_g / stages) & 1;
+          const int tap = it / s.kc;
+          const int c0 = (it - tap * s.kc) * kBK;
+          mbar_wait(&empty_bar[st], ph ^ 1, 1);
+          mbar_expect_tx(&full_bar[st], stage_tx);
+          uint8_t* sa = tiles + (size_t)st * stage_bytes;
+          tma_load_4d(sa, &p.map_a, &full_bar[st], c0, i1_0 + s.tap1[tap], i2_0 + s.tap2[tap], i3 + s.tap3[tap]);
+          tma_load_2d(sa + kABytes, &p.map_b, &full_bar[st], tap * s.c + c0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kBM, BN, 0, 0);
+      uint32_t it_g = 0;
+      uint32_t lt = 0;
+      for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int it = 0; it < k_iters; ++it, ++it_g) {
+          const int st = it_g % stages;
+          const uint32_t ph = (it_g / stages) & 1;
+          mbar_wait(&full_bar[st], ph, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + (size_t)st * stage_bytes);
+          const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
+            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[st]);
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const TapGemmEpilogue& e = p.e;
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;
+    const int rows_in_tile = s.box1 * s.box2;
+    const int out_n = e.geglu ? (s.n >> 1) : s.n;
+    const bool vec_ok = ((e.ldo & 7) == 0) && ((out_n & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0) &&
+                        (e.residual == nullptr ||
+                         (((e.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0)));
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      int nb_i = tile % s.nb;
+      int rest = tile / s.nb;
+      const int t1_i = rest % s.t1;
+      rest /= s.t1;
+      const int t2_i = rest % s.t2;
+      const int i3 = rest / s.t2;
+      const int i1 = t1_i * s.box1 + (r % s.box1);
+      const int i2 = t2_i * s.box2 + (r / s.box1);
+      const bool row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
+      const long row = ((long)i3 * s.d2 + i2) * s.d1 + i1;
+
+      mbar_wait(&tfull_bar[as], aph, 4);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
+
+      if (!e.geglu) {
+        const int n0 = nb_i * BN;
+        __half* orow = e.out + row * e.ldo;
+        const __half* rrow = e.residual ? e.residual + row * e.ldr : nullptr;
+        const __half* grow = e.group_bias ? e.group_bias + (long)i3 * e.ld_group_bias : nullptr;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          const int nbase = n0 + c0;
+          if (nbase >= s.n) continue;
+          if (vec_ok && nbase + 32 <= s.n) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a = __uint_as_float(v[j8 * 8 + j]) * e.alpha;
+                if (e.bias) a += __ldg(e.bias + nbase + j8 * 8 + j);
+                f[j] = a;
+              }
+              if (grow) {
+                // reference: h (fp16 conv output) + emb_out (fp16) -> fp16  (util.py:909-919)
+                const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(grow + nbase + j8 * 8));
+                const __half* gh = reinterpret_cast<const __half*>(&g4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __half2float(__float2half_rn(f[j])) + __half2float(gh[j]);
+              }
+              if (rrow) {
+                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + nbase + j8 * 8));
+                const __half* rh = reinterpret_cast<const __half*>(&r4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __half2float(__float2half_rn(f[j])) + __half2float(rh[j]);
+              }
+              uint4 o;
+              o.x = pack_half2(f[0], f[1]);
+              o.y = pack_half2(f[2], f[3]);
+              o.z = pack_half2(f[4], f[5]);
+              o.w = pack_half2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(orow + nbase + j8 * 8) = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              const int n = nbase + j;
+              if (n >= s.n) break;
+              float a = __uint_as_float(v[j]) * e.alpha;
+              if (e.bias) a += e.bias[n];
+              if (grow) a = __half2float(__float2half_rn(a)) + __half2float(grow[n]);
+              if (rrow) a = __half2float(__float2half_rn(a)) + __half2float(rrow[n]);
+              orow[n] = __float2half_rn(a);
+            }
+          }
+        }
+      } else {
+        // GEGLU: columns [0,BN/2) of this tile are "value" j, columns [BN/2,BN) the matching "gate" j
+        // (host interleaves the weight rows per BN block).  out = value * gelu(gate)   (util.py:707-714)
+        const int hb = BN >> 1;
+        const int o0 = nb_i * hb;
+        __half* orow = e.out + row * e.ldo;
+        for (int c0 = 0; c0 < hb; c0 += 32) {
+          uint32_t v[32], g[32];
+          tmem_ld32(t_row + c0, v);
+          tmem_ld32(t_row + hb + c0, g);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          const int obase = o0 + c0;
+          if (obase >= out_n) continue;
+          const int wbase = nb_i * BN + c0;  // packed weight-row index of value j (gate is + hb)
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(v[j]) * e.alpha;
+            float b = __uint_as_float(g[j]) * e.alpha;
+            if (e.bias) {
+              a += __ldg(e.bias + wbase + j);
+              b += __ldg(e.bias + wbase + hb + j);
+            }
+            // reference rounds the projection to fp16, gelu to fp16, product to fp16
+            const float a16 = __half2float(__float2half_rn(a));
+            const float b16 = __half2float(__float2half_rn(b));
+            const float ge = __half2float(__float2half_rn(gelu_erf(b16)));
+            f[j] = a16 * ge;
+          }
+          if (vec_ok && obase + 32 <= out_n) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint4 o;
+              o.x = pack_half2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+              o.y = pack_half2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+              o.z = pack_half2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+              o.w = pack_half2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(orow + obase + j8 * 8) = o;
+            }
+          } else {
+            for (int j = 0; j < 32 && obase + j < out_n; ++j) orow[obase + j] = __float2half_rn(f[j]);
+          }
+        }
+      }
+      // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
+  const TapGemmShape& s = a.shape;
+  VG_REQUIRE(s.c % 64 == 0, "tapgemm_sm100: C must be a multiple of 64");
+  VG_REQUIRE(s.bn >= 32 && s.bn <= 256 && s.bn % 32 == 0, "tapgemm_sm100: BN must be in [32,256], multiple of 32");
+  VG_REQUIRE(s.box1 >= 1 && s.box2 >= 1 && s.box1 * s.box2 <= kBM && s.box1 <= 256 && s.box2 <= 256,
+             "tapgemm_sm100: bad box");
+  VG_REQUIRE(s.num_taps >= 1 && s.num_taps <= kMaxTaps, "tapgemm_sm100: bad tap count");
+  VG_REQUIRE((reinterpret_cast<uintptr_t>(a.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0,
+             "tapgemm_sm100: A and W must be 16-byte aligned");
+  if (a.epi.geglu) VG_REQUIRE(s.bn % 64 == 0 && s.n % s.bn == 0, "tapgemm_sm100: GEGLU needs BN%64==0 and N%BN==0");
+
+  TapGemmKernelParams p;
+  p.s = s;
+  p.e = a.epi;
+  {
+    const uint64_t dims[4] = {(uint64_t)s.c, (uint64_t)s.d1, (uint64_t)s.d2, (uint64_t)s.d3};
+    const uint64_t strides[3] = {(uint64_t)a.a_stride1 * 2, (uint64_t)a.a_stride2 * 2, (uint64_t)a.a_stride3 * 2};
+    const uint32_t box[4] = {64, (uint32_t)s.box1, (uint32_t)s.box2, 1};
+    int rc = make_tmap_f16(&p.map_a, a.a, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)s.num_taps * s.c, (uint64_t)s.n};
+    const uint64_t strides[1] = {(uint64_t)s.num_taps * s.c * 2};
+    const uint32_t box[2] = {64, (uint32_t)s.bn};
+    int rc = make_tmap_f16(&p.map_b, a.w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  p.b_slot_bytes = ((s.bn * kBK * 2 + 1023) / 1024) * 1024;
+  const int stage_bytes = kABytes + p.b_slot_bytes;
+  const int budget = 200 * 1024;
+  int stages = budget / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  int grid = sm_count();
+  if (grid > s.total_tiles) grid = s.total_tiles;
+  if (grid < 1) return 0;
+  tapgemm_sm100_kernel<<<grid, kThreads, smem, stream>>>(p);
+  VG_LAUNCH_CHECK("tapgemm_sm100_kernel");
+  return 0;
+}
+
+}  // namespace vg

@@ -1,0 +1,83 @@
+"""ctypes binding of libvgen_b200.so (the C ABI declared in include/vgen_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+`VgenError` is raised.  PyTorch is used by callers only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("VGEN_B200_LIB", _PKG / "libvgen_b200.so"))
+
+
+class VgenError(RuntimeError):
+    pass
+
+
+class Epilogue(ctypes.Structure):
+    """struct vgen_epilogue (include/vgen_b200.h)."""
+    _fields_ = [
+        ("alpha", ctypes.c_float),
+        ("bias", ctypes.c_void_p),
+        ("group_bias", ctypes.c_void_p),
+        ("group_bias_ld", ctypes.c_int64),
+        ("residual", ctypes.c_void_p),
+        ("residual_ld", ctypes.c_int64),
+        ("geglu", ctypes.c_int),
+        ("bn", ctypes.c_int),
+    ]
+
+
+_lib = None
+
+_vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+_EP = ctypes.POINTER(Epilogue)
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/vgen_b200.h 1:1.
+_SIGNATURES = {
+    "vgen_abi_version": [],
+    "vgen_last_error": [],
+    "vgen_launch_count": [],
+    "vgen_set_tapgemm_impl": [_i32],
+    "vgen_linear": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _EP, _vp],
+    "vgen_conv2d_3x3": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _EP, _vp],
+    "vgen_tconv3": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _EP, _vp],
+}
+_RESTYPES = {"vgen_last_error": ctypes.c_char_p, "vgen_launch_count": ctypes.c_int64}
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library once; raise VgenError if it is absent (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VgenError(
+            f"{LIB_PATH} not found: build it with `python -m vgen_b200.build` "
+            "(vgen_b200 has no CPU or PyTorch fallback path)")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    if lib.vgen_abi_version() != 1:
+        raise VgenError(f"ABI version mismatch: library {lib.vgen_abi_version()} != binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().vgen_last_error()
+        raise VgenError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load().vgen_launch_count())
