@@ -64,6 +64,70 @@ int vgen_conv2d_3x3(const void* x, int64_t nimg, int64_t h, int64_t w_, int64_t 
 int vgen_tconv3(const void* x, int64_t f, int64_t hw, int64_t c, const void* w, int64_t n, void* out,
                 int64_t ldo, const vgen_epilogue* epi, void* stream);
 
+/* ---- normalisation (norm.cu; HBM-bound, fp32 statistics) ---------------------------------------- */
+/* GroupNorm(32 groups) over x[n][p][c] fp16 (statistics per sample n over p*c/32 values), optional
+ * SiLU, y fp16.  For the 5-D (all-frames-jointly) norms pass n = batch, p = f*h*w.
+ * replaces: nn.GroupNorm(+nn.SiLU) util.py:845-849,867-869,329,1211,1663-1680; autoencoder.py:15-16 */
+int64_t vgen_group_norm_workspace_bytes(int64_t n);
+int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, const float* gamma, const float* beta,
+                    float eps, int silu, void* workspace, void* stream);
+/* LayerNorm over the last dim of x[rows][c] (row strides ldx / ldy).  replaces: nn.LayerNorm util.py:694-696,1429 */
+int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx, int64_t ldy, const float* gamma,
+                    const float* beta, float eps, void* stream);
+
+/* ---- attention ---------------------------------------------------------------------------------- */
+/* softmax(q k^T * scale) v, head_dim 64, no mask (attn_sm100.cu, tcgen05 + TMEM).  q[batch][lq][heads*64]
+ * with token stride ldq (so q/k/v may be column slices of one fused projection buffer); k/v have
+ * batch / kv_batch_div batches (a context shared by the frames of a video is stored once).
+ * replaces: xformers.ops.memory_efficient_attention, util.py:254-259 (spatial self / cross attention) */
+int vgen_attention_d64(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
+                       int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                       int64_t kv_batch_div, float scale, void* stream);
+/* Per-pixel attention over L <= 32 frames (attn_temporal.cu, register-resident mma.sync): token t of
+ * sequence s lives at q + s*seq_stride + t*tok_stride (+ head*head_dim).  head_dim 64 is the fast path;
+ * any head_dim <= 64, L <= 64 is served by a scalar kernel (I2VGen's 4-channel local encoder).
+ * replaces: memory_efficient_attention in TemporalTransformer util.py:1258-1261; Attention util.py:1396-1424 */
+int vgen_attention_temporal(const void* q, const void* k, const void* v, void* out, int64_t nseq, int64_t heads,
+                            int64_t L, int64_t head_dim, int64_t tok_stride, int64_t seq_stride,
+                            int64_t tok_stride_o, int64_t seq_stride_o, float scale, void* stream);
+/* in-place softmax(x * scale) over rows of x[rows][n] fp16 (VAE AttnBlock, autoencoder.py:377-379) */
+int vgen_softmax_rows(void* x, int64_t rows, int64_t n, int64_t ld, float scale, void* stream);
+
+/* ---- data movement / pointwise (elementwise.cu) ------------------------------------------------- */
+/* x[n][c][p] (fp32 or fp16) -> y[n][p][c_pad] fp16 (extra channels zero): 'b c f h w -> (b f) h w c' */
+int vgen_cp_to_pc(const void* x, int x_is_f32, void* y, int64_t n, int64_t c, int64_t p, int64_t c_pad, void* stream);
+/* x[n][p][ldx] fp16 (first c channels) -> y[n][c][p] (fp16 or fp32) */
+int vgen_pc_to_cp(const void* x, int64_t ldx, void* y, int y_is_f32, int64_t n, int64_t c, int64_t p, void* stream);
+/* channels-last im2col with zero padding (optionally SiLU on the gathered input); columns beyond
+ * kh*kw*c up to kpad are zero.  Serves stride-2 / tiny-channel convs (Downsample util.py:946, first
+ * conv unet_t2v.py:112, I2VGen conditioning convs unet_i2vgen.py:116-132, VAE conv_in) via vgen_linear */
+int vgen_im2col(const void* x, void* out, int64_t nimg, int64_t h, int64_t w, int64_t c, int64_t kh, int64_t kw,
+                int64_t stride, int64_t pad_t, int64_t pad_l, int64_t ho, int64_t wo, int64_t kpad, int act_silu,
+                void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest') on [nimg][h][w][c] (util.py:768, autoencoder.py:455) */
+int vgen_upsample_nearest2x(const void* x, void* y, int64_t nimg, int64_t h, int64_t w, int64_t c, void* stream);
+/* dst[r][0:cols] = src[r][0:cols] with row strides (torch.cat along channels, unet_t2v.py:269) */
+int vgen_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, void* stream);
+/* op: 0 silu(a), 1 a+b, 2 gelu(a), 3 a*s, 4 a+s*b  (fp16, fp32 math) */
+int vgen_eltwise(int op, const void* a, const void* b, void* y, int64_t n, float s, void* stream);
+/* out = [gelu](silu_in?(a) @ w^T + bias) [+ res] for small m or tiny k (time / fps / context MLPs
+ * unet_t2v.py:93-104, ResBlock emb_layers util.py:857-863, TransformerV2 linears util.py:1396-1452) */
+int vgen_linear_small(const void* a, int64_t m, int64_t k, int64_t lda, const void* w, const float* bias, int64_t n,
+                      const void* res, int64_t ldr, void* out, int64_t ldo, int silu_in, int gelu_out, void* stream);
+/* sinusoidal_embedding util.py:178-190: out[b][dim] fp16 = cat[cos, sin](t * 10000^(-i/half)) */
+int vgen_sinusoidal_embedding(const float* t, void* out, int64_t b, int64_t dim, void* stream);
+/* nn.AdaptiveAvgPool2d on channels-last input, optional SiLU on the input (unet_i2vgen.py:128-129) */
+int vgen_adaptive_avgpool(const void* x, void* y, int64_t nimg, int64_t h, int64_t w, int64_t c, int64_t oh, int64_t ow,
+                          int silu_in, void* stream);
+
+/* ---- sampler ------------------------------------------------------------------------------------ */
+/* One fused DDIM update (diffusion_ddim.py:157-162 CFG mix, :194-196 v->x0 | :190-192 eps->x0, :230-240):
+ *   out = u + g*(y-u) in fp16 (u NULL: out = y); x0; eps; xt <- c4*x0 + c5*eps (+ c6*noise).
+ * coef7 = {sqrt_ab[t], sqrt(1-ab[t]), sqrt(1/ab[t]), sqrt(1/ab[t]-1), sqrt(ab_prev), sqrt(1-ab_prev-sigma^2),
+ *          sigma*mask} as fp32 (the host keeps the fp64 tables; timestep/index math is bit-exact there). */
+int vgen_ddim_step(float* xt, const void* y, const void* u, const float* noise, int64_t n, float guide_scale,
+                   const float* coef7, int mean_type_v, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

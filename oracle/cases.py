@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE ONLY -- the parity cases: constructor kwargs, weight seed and input recipe.
+
+Small cases run the REAL reference on CPU in seconds (oracle/make_golden.py) and are replayed on the
+GPU against the stored outputs.  Constructor kwargs are the reference's own (UNetSD_T2VBase /
+UNetSD_I2VGen / AutoencoderKL); note the decoder's SpatialTransformers hard-code context_dim=1024
+(tools/modules/unet/unet_t2v.py:180), so every case uses 1024-wide context tokens.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import synth
+
+_T2V_TINY = dict(in_dim=4, dim=64, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2], num_heads=2,
+                 head_dim=64, num_res_blocks=1, attn_scales=[1.0, 0.5], dropout=0.1, temporal_attention=True,
+                 temporal_attn_times=1, use_checkpoint=False, use_fps_condition=False, use_sim_mask=False)
+_I2V_TINY = dict(_T2V_TINY, concat_dim=4)
+_VAE_TINY = dict(ddconfig=dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=32,
+                               ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[], dropout=0.0), embed_dim=4)
+
+# the effective constructor kwargs of the BASELINE configs
+_FULL_UNET = dict(in_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
+                  head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], dropout=0.1, temporal_attention=True,
+                  temporal_attn_times=1, use_checkpoint=True, use_fps_condition=False, use_sim_mask=False)
+_FULL_VAE = dict(ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                               ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0), embed_dim=4)
+
+FULL_CTORS = {
+    "full_t2v": ("t2v", _FULL_UNET),
+    "full_i2vgen": ("i2vgen", dict(_FULL_UNET, concat_dim=4)),
+    "full_vae": ("vae", _FULL_VAE),
+}
+
+CASES = {
+    # name: kind, ctor kwargs, weight seed, input shape recipe
+    "t2v_tiny": dict(kind="t2v", ctor=_T2V_TINY, seed=11, b=1, f=4, h=8, w=12, ntok=5, t=[481],
+                     ddim=dict(steps=4, guide_scale=9.0)),
+    "t2v_tiny_b2": dict(kind="t2v", ctor=_T2V_TINY, seed=12, b=2, f=3, h=10, w=6, ntok=7, t=[751, 21]),
+    "i2vgen_tiny": dict(kind="i2vgen", ctor=_I2V_TINY, seed=13, b=1, f=4, h=8, w=12, ntok=5, t=[961],
+                        ddim=dict(steps=4, guide_scale=9.0)),
+    "vae_tiny": dict(kind="vae", ctor=_VAE_TINY, seed=14, n=2, h=8, w=12),
+}
+
+
+def make_inputs(case):
+    """Deterministic inputs (numpy PCG64 keyed by tensor name, like the weights)."""
+    s = case["seed"] + 1000
+    if case["kind"] == "vae":
+        return {"z": synth.tensor("z", (case["n"], 4, case["h"], case["w"]), 1.0, s)}
+    b, f, h, w, L = case["b"], case["f"], case["h"], case["w"], case["ntok"]
+    d = {
+        "x": synth.tensor("x", (b, 4, f, h, w), 1.0, s),
+        "t": torch.tensor(case["t"], dtype=torch.long),
+        "y": synth.tensor("y", (b, L, 1024), 1.0, s),
+        "y_neg": synth.tensor("y_neg", (b, L, 1024), 1.0, s),
+    }
+    if case["kind"] == "i2vgen":
+        d["image"] = synth.tensor("image", (b, 1, 1024), 1.0, s)
+        li = synth.tensor("local_image", (b, 4, 1, h, w), 0.18215, s)
+        d["local_image"] = li.repeat(1, 1, f, 1, 1)
+        d["fps"] = torch.tensor([16] * b, dtype=torch.long)
+    return d

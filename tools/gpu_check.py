@@ -157,9 +157,214 @@ def group_tapgemm_simt():
     group_tapgemm("simt")
 
 
+def group_norm_checks():
+    from vgen_b200 import ops
+    F = torch.nn.functional
+    g = torch.Generator(device="cpu").manual_seed(2)
+
+    def rnd(*s, scale=1.0, shift=0.0):
+        return (torch.randn(*s, generator=g) * scale + shift).cuda()
+
+    for (n, p, c, eps, silu, shift) in [(2, 96, 64, 1e-5, True, 0.0), (16, 220, 1280, 1e-5, True, 0.5), (1, 16 * 880, 640, 1e-6, False, 3.0),
+                                        (3, 3520, 320, 1e-5, True, 0.0), (2, 300, 2560, 1e-5, True, -1.0), (2, 1000, 1920, 1e-5, True, 0.0),
+                                        (2, 5000, 32, 1e-6, True, 10.0), (1, 14080, 960, 1e-5, True, 0.0), (2, 4096, 128, 1e-6, True, 0.0)]:
+        def f():
+            x = rnd(n, p, c, scale=1.5, shift=shift).half()
+            ga, be = rnd(c, scale=0.2, shift=1.0), rnd(c, scale=0.2)
+            y = ops.group_norm(x, ga, be, eps, silu)
+            torch.cuda.synchronize()
+            ref = F.group_norm(x.float().permute(0, 2, 1), 32, ga, be, eps)
+            if silu:
+                ref = F.silu(ref)
+            report(f"group_norm n{n} p{p} c{c} silu{int(silu)} shift{shift}", rel_err(y, ref.permute(0, 2, 1)), 2e-3)
+        run_case(f"gn {n} {p} {c}", f)
+
+    for (rows, c) in [(1000, 320), (777, 640), (4096, 1280), (100, 512), (5000, 4), (33, 2560), (64, 64)]:
+        def f():
+            x = rnd(rows, c, scale=2.0, shift=0.3).half()
+            ga, be = rnd(c, scale=0.2, shift=1.0), rnd(c, scale=0.2)
+            y = ops.layer_norm(x, ga, be)
+            torch.cuda.synchronize()
+            report(f"layer_norm rows{rows} c{c}", rel_err(y, F.layer_norm(x.float(), (c,), ga, be, 1e-5)), 2e-3)
+        run_case(f"ln {rows} {c}", f)
+
+
+def group_attention():
+    from vgen_b200 import ops
+    F = torch.nn.functional
+    g = torch.Generator(device="cpu").manual_seed(3)
+
+    def rnd(*s, scale=1.0):
+        return (torch.randn(*s, generator=g) * scale).cuda()
+
+    def sdpa(q, k, v, heads):
+        b, lq, inner = q.shape
+        d = inner // heads
+        sp = lambda t: t.float().reshape(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3)  # noqa: E731
+        o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v))
+        return o.permute(0, 2, 1, 3).reshape(b, lq, inner)
+
+    for (b, heads, lq, lk, div, fused) in [(1, 1, 128, 128, 1, False), (1, 1, 256, 128, 1, False), (1, 1, 256, 256, 1, False),
+                                           (2, 2, 300, 300, 1, True), (2, 5, 880, 880, 1, True), (4, 5, 220, 77, 4, False),
+                                           (4, 10, 3520, 145, 2, False), (1, 5, 14080, 14080, 1, True), (3, 1, 96, 96, 1, True),
+                                           (2, 2, 1000, 1, 1, False)]:
+        def f():
+            inner = heads * 64
+            if fused:
+                qkv = rnd(b, lq, 3 * inner, scale=1.0).half()
+                q, k, v = qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:]
+            else:
+                q = rnd(b, lq, inner).half()
+                kv = rnd(b // div, lk, 2 * inner).half()
+                k, v = kv[:, :, :inner], kv[:, :, inner:]
+            out = ops.attention_d64(q, k, v, heads, kv_batch_div=div)
+            torch.cuda.synchronize()
+            kk = k.repeat_interleave(div, dim=0)
+            vv = v.repeat_interleave(div, dim=0)
+            report(f"attention_d64 b{b} h{heads} lq{lq} lk{lk} div{div} fused{int(fused)}", rel_err(out, sdpa(q, kk, vv, heads)), 3e-3)
+        run_case(f"attn {b} {heads} {lq} {lk}", f)
+
+    for (f_, npix, heads, d) in [(16, 100, 1, 64), (16, 1000, 5, 64), (8, 333, 2, 64), (4, 96, 2, 64), (3, 60, 1, 64),
+                                 (32, 500, 5, 64), (20, 64, 2, 64), (16, 14080, 8, 64), (16, 300, 2, 4), (4, 50, 2, 4)]:
+        def f():
+            inner = heads * d
+            qkv = rnd(f_, npix, 3 * inner).half()
+            q, k, v = qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:]
+            out = ops.attention_temporal(q, k, v, heads, d)
+            torch.cuda.synchronize()
+            tq = lambda t: t.permute(1, 0, 2)  # noqa: E731  [npix, f, inner]
+            ref = sdpa(tq(q), tq(k), tq(v), heads).permute(1, 0, 2)
+            report(f"attention_temporal f{f_} npix{npix} h{heads} d{d}", rel_err(out, ref), 3e-3)
+        run_case(f"tattn {f_} {npix}", f)
+
+    def f():
+        x = rnd(700, 1500, scale=3.0).half()
+        ref = torch.softmax(x.float() * 0.25, dim=-1)
+        ops.softmax_rows_(x, 0.25)
+        torch.cuda.synchronize()
+        report("softmax_rows 700x1500", rel_err(x, ref), 2e-3)
+    run_case("softmax", f)
+
+
+def group_elementwise():
+    from vgen_b200 import ops
+    F = torch.nn.functional
+    g = torch.Generator(device="cpu").manual_seed(4)
+
+    def rnd(*s, scale=1.0):
+        return (torch.randn(*s, generator=g) * scale).cuda()
+
+    def f():
+        x = rnd(2, 4, 3, 8, 12)
+        y = ops.cp_to_pc(x.reshape(2, 4, -1), 2, 4, 3 * 8 * 12, c_pad=8)
+        torch.cuda.synchronize()
+        ref = torch.zeros(2, 288, 8, device="cuda")
+        ref[:, :, :4] = x.reshape(2, 4, 288).permute(0, 2, 1)
+        report("cp_to_pc fp32 pad8", rel_err(y, ref.half()), 1e-6)
+        z = ops.pc_to_cp(y, 2, 4, 288, torch.float32)
+        torch.cuda.synchronize()
+        report("pc_to_cp fp32", rel_err(z, x.reshape(2, 4, 288).half().float()), 1e-6)
+    run_case("layout", f)
+
+    for (nimg, h, w, c, n, stride, act) in [(2, 8, 12, 8, 64, 1, False), (2, 16, 20, 64, 128, 2, False), (1, 9, 13, 4, 16, 1, True),
+                                            (3, 32, 32, 32, 64, 2, True), (2, 11, 21, 320, 320, 2, False)]:
+        def f():
+            x = rnd(nimg, h, w, c).half()
+            wt = rnd(n, c, 3, 3, scale=(9 * c) ** -0.5).half()
+            b = rnd(n)
+            ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+            kpad = ((9 * c + 63) // 64) * 64
+            col = ops.im2col(x, 3, 3, stride, 1, 1, ho, wo, kpad, act_silu=act)
+            wp = torch.zeros(n, kpad, device="cuda", dtype=torch.float16)
+            wp[:, :9 * c] = wt.permute(0, 2, 3, 1).reshape(n, 9 * c)
+            out = ops.linear(col, wp, bias=b).reshape(nimg, ho, wo, n)
+            torch.cuda.synchronize()
+            xin = x.float().permute(0, 3, 1, 2)
+            if act:
+                xin = F.silu(xin).half().float()
+            ref = F.conv2d(xin, wt.float(), b, stride=stride, padding=1).permute(0, 2, 3, 1)
+            report(f"im2col+linear n{nimg} {h}x{w} c{c}->{n} s{stride} silu{int(act)}", rel_err(out, ref), 2e-3)
+        run_case(f"im2col {h}x{w} c{c}", f)
+
+    def f():
+        x = rnd(2, 5, 7, 64).half()
+        y = ops.upsample_nearest2x(x)
+        torch.cuda.synchronize()
+        ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+        report("upsample_nearest2x", rel_err(y, ref), 1e-6)
+        a, b = rnd(100, 320).half(), rnd(100, 640).half()
+        c = ops.concat_channels(a, b)
+        torch.cuda.synchronize()
+        report("concat_channels", rel_err(c, torch.cat([a, b], -1)), 1e-6)
+        a2, b2 = rnd(33, 4).half(), rnd(33, 4).half()
+        c2 = ops.concat_channels(a2, b2)
+        torch.cuda.synchronize()
+        report("concat_channels small", rel_err(c2, torch.cat([a2, b2], -1)), 1e-6)
+        report("eltwise silu", rel_err(ops.eltwise("silu", a), F.silu(a.float())), 2e-3)
+        report("eltwise gelu", rel_err(ops.eltwise("gelu", a), F.gelu(a.float())), 2e-3)
+        report("eltwise axpy", rel_err(ops.eltwise("axpy", a, a, s=1.0), 2 * a.float()), 2e-3)
+    run_case("misc", f)
+
+    for (m, k, n, silu, gelu, res) in [(1, 320, 1280, False, False, False), (2, 1280, 1280, True, False, False), (3, 1024, 4096, True, False, False),
+                                       (5000, 4, 24, False, False, False), (5000, 8, 4, False, False, True), (5000, 4, 16, False, True, False)]:
+        def f():
+            a = rnd(m, k).half()
+            w = rnd(n, k, scale=k ** -0.5).half()
+            b = rnd(n)
+            r = rnd(m, n).half() if res else None
+            out = ops.linear_small(a, w, b, residual=r, silu_in=silu, gelu_out=gelu)
+            torch.cuda.synchronize()
+            ain = F.silu(a.float()).half().float() if silu else a.float()
+            ref = ain @ w.float().t() + b
+            if gelu:
+                ref = F.gelu(ref.half().float())
+            if res:
+                ref = ref.half().float() + r.float()
+            report(f"linear_small m{m} k{k} n{n} silu{int(silu)} gelu{int(gelu)} res{int(res)}", rel_err(out, ref), 2e-3)
+        run_case(f"linear_small {m} {k} {n}", f)
+
+    def f():
+        t = torch.tensor([981, 1, 500], device="cuda")
+        e = ops.sinusoidal_embedding(t, 320)
+        torch.cuda.synchronize()
+        half = 160
+        tf = t.float()
+        sin = torch.outer(tf, torch.pow(10000, -torch.arange(half, device="cuda").to(tf).div(half)))
+        ref = torch.cat([torch.cos(sin), torch.sin(sin)], dim=1)
+        report("sinusoidal_embedding", (e.float() - ref).abs().max().item(), 2e-3)
+        x = rnd(2, 11, 20, 32).half()
+        y = ops.adaptive_avgpool(x, 32, 32, silu_in=True)
+        torch.cuda.synchronize()
+        ref = F.adaptive_avg_pool2d(F.silu(x.float()).half().float().permute(0, 3, 1, 2), (32, 32)).permute(0, 2, 3, 1)
+        report("adaptive_avgpool 11x20->32x32", rel_err(y, ref), 2e-3)
+        x = rnd(1, 88, 160, 32).half()
+        y = ops.adaptive_avgpool(x, 32, 32)
+        torch.cuda.synchronize()
+        ref = F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), (32, 32)).permute(0, 2, 3, 1)
+        report("adaptive_avgpool 88x160->32x32", rel_err(y, ref), 2e-3)
+    run_case("embed/pool", f)
+
+    def f():
+        xt = rnd(1, 4, 4, 8, 12)
+        y, u = rnd(1, 4, 4, 8, 12).half(), rnd(1, 4, 4, 8, 12).half()
+        coef = [0.6, 0.8, 1.0 / 0.6, (1 / 0.36 - 1) ** 0.5, 0.7, (1 - 0.49) ** 0.5, 0.0]
+        out = u + 9.0 * (y - u)           # fp16 tensor arithmetic, like the reference under autocast
+        ct = [torch.tensor(v, device="cuda", dtype=torch.float32) for v in coef]  # _i() yields fp32 tensors
+        x0 = ct[0] * xt - ct[1] * out
+        eps = (ct[2] * xt - x0) / ct[3]
+        ref = ct[4] * x0 + ct[5] * eps
+        got = ops.ddim_step_(xt.clone(), y, u, coef, 9.0, True)
+        torch.cuda.synchronize()
+        report("ddim_step cfg v-pred", rel_err(got, ref), 1e-5)
+    run_case("ddim", f)
+
+
 GROUPS = {
     "tapgemm": group_tapgemm,
     "tapgemm_simt": group_tapgemm_simt,
+    "norm": group_norm_checks,
+    "attention": group_attention,
+    "elementwise": group_elementwise,
 }
 
 
@@ -167,13 +372,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", default=None)
     ap.add_argument("--all", action="store_true")
+    ap.add_argument("--only", default=None, help="comma-separated group names for --all")
     ap.add_argument("--timeout", type=int, default=240)
     ap.add_argument("--out", default="gpurun_out/gpu_check.json")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     if args.all:
         summary = {}
-        for name in GROUPS:
+        names = args.only.split(",") if args.only else list(GROUPS)
+        for name in names:
             out = args.out.replace(".json", f".{name}.json")
             t0 = time.time()
             try:

@@ -1,0 +1,351 @@
+// GroupNorm(32) (+SiLU) and LayerNorm on channels-last fp16 activations: HBM-bound kernels with
+// 16-byte vectorised, fully coalesced accesses and fp32 statistics.
+//
+// Reference ops replaced:
+//   nn.GroupNorm(32, C) + nn.SiLU in ResBlock in_layers/out_layers   tools/modules/unet/util.py:845-876
+//   GroupNorm over 5-D [b,c,f,h,w] (statistics span ALL frames)       util.py:1248 (TemporalTransformer),
+//                                                                      util.py:1662-1680 (TemporalConvBlock_v2)
+//   GroupNorm eps=1e-6 in SpatialTransformer / VAE                     util.py:329, autoencoder.py:15-16
+//   nn.LayerNorm in BasicTransformerBlock                              util.py:694-696
+// Under the reference's autocast these run in fp32 and the result is rounded to fp16 once by the
+// consuming conv/linear; the kernels below do the same (fp32 maths, one fp16 rounding at the store).
+//
+// GroupNorm is two launches:
+//   gn_stats : grid (splits, N): per-channel fp32 sum / sum-of-squares in registers (each thread owns
+//              fixed channel vectors, so no atomics), folded to per-group (mean, M2) partials.
+//   gn_apply : combines the partials with Chan's formula (robust to mean >> std), then
+//              y = silu?(x * scale_c + shift_c) streamed with 16-byte loads/stores.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vg {
+
+static constexpr int kGroups = 32;
+static constexpr int kMaxSplits = 64;
+
+struct GnGeom {
+  int C, C8, cpg;      // channels, C/8, channels per group
+  int vpt;             // channel vectors per thread
+  int cols;            // thread columns (= ceil(C8 / vpt))
+  int rows;            // pixel rows processed per block iteration
+  long P;              // positions per sample
+  int splits;
+  long chunk;          // positions per split
+};
+
+template <int VPT>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, float2* __restrict__ partial, GnGeom g) {
+  extern __shared__ float sm[];  // [2][rows][C]
+  const int n = blockIdx.y, sp = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int r = tid / g.cols, cv = tid - r * g.cols;
+  const long p0 = (long)sp * g.chunk;
+  long p1 = p0 + g.chunk;
+  if (p1 > g.P) p1 = g.P;
+  float s[VPT][8], q[VPT][8];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[j][i] = q[j][i] = 0.f;
+
+  if (r < g.rows) {
+    const __half* base = x + ((long)n * g.P) * g.C;
+    for (long p = p0 + r; p < p1; p += g.rows) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        const int v = cv + j * g.cols;
+        if (v < g.C8) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * g.C + v * 8));
+          const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            s[j][2 * i] += f.x;
+            q[j][2 * i] += f.x * f.x;
+            s[j][2 * i + 1] += f.y;
+            q[j][2 * i + 1] += f.y * f.y;
+          }
+        }
+      }
+    }
+    float* ss = sm + (long)r * g.C;
+    float* qq = sm + (long)(g.rows + r) * g.C;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int v = cv + j * g.cols;
+      if (v < g.C8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ss[v * 8 + i] = s[j][i];
+          qq[v * 8 + i] = q[j][i];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < kGroups) {
+    float S = 0.f, Q = 0.f;
+    for (int rr = 0; rr < g.rows; ++rr) {
+      const float* ss = sm + (long)rr * g.C + tid * g.cpg;
+      const float* qq = sm + (long)(g.rows + rr) * g.C + tid * g.cpg;
+      for (int c = 0; c < g.cpg; ++c) {
+        S += ss[c];
+        Q += qq[c];
+      }
+    }
+    const float cnt = (float)((p1 > p0 ? p1 - p0 : 0) * g.cpg);
+    const float mean = cnt > 0 ? S / cnt : 0.f;
+    float m2 = Q - S * mean;  // sum (x-mean)^2
+    if (m2 < 0.f) m2 = 0.f;
+    partial[((long)n * g.splits + sp) * kGroups + tid] = make_float2(mean, m2);
+  }
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                       const float2* __restrict__ partial,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       GnGeom g, float eps, int silu, long apply_chunk) {
+  extern __shared__ float sm[];  // scale[C], shift[C], mean[32], rstd[32]
+  float* scale = sm;
+  float* shift = sm + g.C;
+  float* gmean = sm + 2 * g.C;
+  float* grstd = gmean + kGroups;
+  const int n = blockIdx.y;
+  if (threadIdx.x < kGroups) {
+    // Chan et al. parallel combination of (count, mean, M2)
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    for (int sp = 0; sp < g.splits; ++sp) {
+      const long q0 = (long)sp * g.chunk;
+      long q1 = q0 + g.chunk;
+      if (q1 > g.P) q1 = g.P;
+      if (q1 <= q0) continue;
+      const float cb = (float)((q1 - q0) * g.cpg);
+      const float2 pm = partial[((long)n * g.splits + sp) * kGroups + threadIdx.x];
+      const float tot = cnt + cb;
+      const float delta = pm.x - mean;
+      mean += delta * (cb / tot);
+      m2 += pm.y + delta * delta * (cnt * cb / tot);
+      cnt = tot;
+    }
+    gmean[threadIdx.x] = mean;
+    grstd[threadIdx.x] = rsqrtf(m2 / cnt + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    const int grp = c / g.cpg;
+    const float sc = grstd[grp] * gamma[c];
+    scale[c] = sc;
+    shift[c] = beta[c] - gmean[grp] * sc;
+  }
+  __syncthreads();
+  const long p0 = (long)blockIdx.x * apply_chunk;
+  long p1 = p0 + apply_chunk;
+  if (p1 > g.P) p1 = g.P;
+  const long nvec = (p1 - p0) * g.C8;
+  const __half* xb = x + ((long)n * g.P + p0) * g.C;
+  __half* yb = y + ((long)n * g.P + p0) * g.C;
+  for (long i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int v = (int)(i % g.C8);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 t = __half22float2(h2[k]);
+      f[2 * k] = t.x;
+      f[2 * k + 1] = t.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = f[k] * scale[v * 8 + k] + shift[v * 8 + k];
+      f[k] = silu ? silu_f(t) : t;
+    }
+    uint4 o;
+    o.x = pack_half2(f[0], f[1]);
+    o.y = pack_half2(f[2], f[3]);
+    o.z = pack_half2(f[4], f[5]);
+    o.w = pack_half2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(yb + i * 8) = o;
+  }
+}
+
+static int gn_geometry(long N, long P, int C, GnGeom* g) {
+  VG_REQUIRE(C % 32 == 0 && C % 8 == 0, "group_norm: C must be a multiple of 32");
+  g->C = C;
+  g->C8 = C / 8;
+  g->cpg = C / kGroups;
+  g->vpt = (g->C8 + 255) / 256;
+  VG_REQUIRE(g->vpt <= 2, "group_norm: C > 4096 not supported");
+  g->cols = (g->C8 + g->vpt - 1) / g->vpt;
+  g->rows = 256 / g->cols;
+  if (g->rows < 1) g->rows = 1;
+  g->P = P;
+  long want = (4L * sm_count()) / (N > 0 ? N : 1);
+  if (want < 1) want = 1;
+  if (want > kMaxSplits) want = kMaxSplits;
+  long min_chunk = 4L * g->rows;  // at least a few iterations per block
+  long chunk = (P + want - 1) / want;
+  if (chunk < min_chunk) chunk = min_chunk;
+  g->chunk = chunk;
+  g->splits = (int)((P + chunk - 1) / chunk);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- LayerNorm
+// one warp per row; the row lives in registers (C <= 2560), two-pass mean / variance like ATen.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        long rows, int C, long ldx, long ldy, float eps) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int C8 = C >> 3;
+  const __half* xr = x + row * ldx;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < C8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = __half22float2(h2[k]);
+        f[j][2 * k] = t.x;
+        f[j][2 * k + 1] = t.y;
+        s += t.x + t.y;
+      }
+    }
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < C8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = f[j][k] - mean;
+        q += d * d;
+      }
+    }
+  }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  __half* yr = y + row * ldy;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < C8) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (f[j][k] - mean) * rstd * __ldg(gamma + v * 8 + k) + __ldg(beta + v * 8 + k);
+      uint4 u;
+      u.x = pack_half2(o[0], o[1]);
+      u.y = pack_half2(o[2], o[3]);
+      u.z = pack_half2(o[4], o[5]);
+      u.w = pack_half2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + v * 8) = u;
+    }
+  }
+}
+
+// generic small-C LayerNorm (any C, scalar): one thread per row
+__global__ void layernorm_small_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, long rows, int C,
+                                       long ldx, long ldy, float eps) {
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const __half* xr = x + row * ldx;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += __half2float(xr[c]);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = __half2float(xr[c]) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(q / C + eps);
+  for (int c = 0; c < C; ++c) y[row * ldy + c] = __float2half_rn((__half2float(xr[c]) - mean) * rstd * gamma[c] + beta[c]);
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" {
+
+int64_t vgen_group_norm_workspace_bytes(int64_t n) { return (n < 1 ? 1 : n) * (int64_t)kMaxSplits * kGroups * sizeof(float2); }
+
+int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, const float* gamma, const float* beta,
+                    float eps, int silu, void* workspace, void* stream) {
+  VG_REQUIRE(x && y && gamma && beta && workspace, "vgen_group_norm: null pointer");
+  VG_REQUIRE(n >= 0 && p > 0 && c > 0, "vgen_group_norm: bad shape");
+  if (n == 0) return 0;
+  VG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+             "vgen_group_norm: x/y must be 16-byte aligned");
+  GnGeom g;
+  int rc = gn_geometry(n, p, (int)c, &g);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float2* part = reinterpret_cast<float2*>(workspace);
+  const size_t smem_stats = (size_t)2 * g.rows * g.C * sizeof(float);
+  VG_REQUIRE(smem_stats <= 48 * 1024, "vgen_group_norm: stats smem too large");
+  dim3 grid_s(g.splits, (unsigned)n);
+  const int threads = g.rows * g.cols < 32 ? 32 : g.rows * g.cols;
+  if (g.vpt == 1)
+    gn_stats_kernel<1><<<grid_s, threads, smem_stats, st>>>(reinterpret_cast<const __half*>(x), part, g);
+  else
+    gn_stats_kernel<2><<<grid_s, threads, smem_stats, st>>>(reinterpret_cast<const __half*>(x), part, g);
+  VG_LAUNCH_CHECK("gn_stats_kernel");
+  // apply: ~4 waves of blocks
+  long blocks = (4L * sm_count()) / n;
+  if (blocks < 1) blocks = 1;
+  long apply_chunk = (p + blocks - 1) / blocks;
+  if (apply_chunk < 8) apply_chunk = 8;
+  blocks = (p + apply_chunk - 1) / apply_chunk;
+  dim3 grid_a((unsigned)blocks, (unsigned)n);
+  const size_t smem_apply = (size_t)(2 * g.C + 2 * kGroups) * sizeof(float);
+  gn_apply_kernel<<<grid_a, 256, smem_apply, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), part,
+                                                   gamma, beta, g, eps, silu, apply_chunk);
+  VG_LAUNCH_CHECK("gn_apply_kernel");
+  return 0;
+}
+
+int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx, int64_t ldy, const float* gamma,
+                    const float* beta, float eps, void* stream) {
+  VG_REQUIRE(x && y && gamma && beta, "vgen_layer_norm: null pointer");
+  VG_REQUIRE(rows >= 0 && c > 0 && ldx >= c && ldy >= c, "vgen_layer_norm: bad shape");
+  if (rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __half* xp = reinterpret_cast<const __half*>(x);
+  __half* yp = reinterpret_cast<__half*>(y);
+  const bool vec = (c % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && c <= 2560;
+  if (vec) {
+    const int wpb = 8;
+    const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
+    const int c8 = (int)c / 8;
+    if (c8 <= 32)
+      layernorm_kernel<1><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+    else if (c8 <= 64)
+      layernorm_kernel<2><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+    else if (c8 <= 160)
+      layernorm_kernel<5><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+    else
+      layernorm_kernel<10><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+    VG_LAUNCH_CHECK("layernorm_kernel");
+  } else {
+    const unsigned blocks = (unsigned)((rows + 127) / 128);
+    layernorm_small_kernel<<<blocks, 128, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+    VG_LAUNCH_CHECK("layernorm_small_kernel");
+  }
+  return 0;
+}
+
+}  // extern "C"

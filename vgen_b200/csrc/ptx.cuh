@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-__device__ __noinline__ void mbar_deadlock(int tag, uint32_t parity) {
+static __device__ __noinline__ void mbar_deadlock(int tag, uint32_t parity) {
   printf("[vgen_b200] mbarrier wait timed out: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
          (int)threadIdx.x, tag, parity);
   __trap();
@@ -183,6 +183,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -45,8 +45,25 @@ _SIGNATURES = {
     "vgen_linear": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _EP, _vp],
     "vgen_conv2d_3x3": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _EP, _vp],
     "vgen_tconv3": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _EP, _vp],
+    "vgen_group_norm_workspace_bytes": [_i64],
+    "vgen_group_norm": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _f32, _i32, _vp, _vp],
+    "vgen_layer_norm": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _f32, _vp],
+    "vgen_attention_d64": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
+    "vgen_attention_temporal": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
+    "vgen_softmax_rows": [_vp, _i64, _i64, _i64, _f32, _vp],
+    "vgen_cp_to_pc": [_vp, _i32, _vp, _i64, _i64, _i64, _i64, _vp],
+    "vgen_pc_to_cp": [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp],
+    "vgen_im2col": [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp],
+    "vgen_upsample_nearest2x": [_vp, _vp, _i64, _i64, _i64, _i64, _vp],
+    "vgen_copy2d": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
+    "vgen_eltwise": [_i32, _vp, _vp, _vp, _i64, _f32, _vp],
+    "vgen_linear_small": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp],
+    "vgen_sinusoidal_embedding": [_vp, _vp, _i64, _i64, _vp],
+    "vgen_adaptive_avgpool": [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp],
+    "vgen_ddim_step": [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _i32, _vp],
 }
-_RESTYPES = {"vgen_last_error": ctypes.c_char_p, "vgen_launch_count": ctypes.c_int64}
+_RESTYPES = {"vgen_last_error": ctypes.c_char_p, "vgen_launch_count": ctypes.c_int64,
+             "vgen_group_norm_workspace_bytes": ctypes.c_int64}
 
 
 def declared_symbols():

@@ -141,3 +141,215 @@ def pack_geglu_weight(w, bias, bn):
         bg = bias[inner:].reshape(inner // hb, hb)
         bp = torch.cat([bv, bg], dim=1).reshape(two_inner).contiguous()
     return wp, bp
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+_gn_ws = {}
+
+
+def _gn_workspace(device, n):
+    need = int(_l.load().vgen_group_norm_workspace_bytes(n))
+    ws = _gn_ws.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=device, dtype=torch.uint8)
+        _gn_ws[device] = ws
+    return ws
+
+
+def group_norm(x, gamma, beta, eps, silu, n=None, out=None):
+    """x [..., c] fp16 channels-last; statistics per sample over everything but the leading `n` dim.
+    x is viewed as [n, p, c]: pass n explicitly when the leading dims are not (n, ...)."""
+    _chk16(x, "x")
+    if not x.is_contiguous():
+        raise _l.VgenError("group_norm: x must be contiguous")
+    c = x.shape[-1]
+    n = x.shape[0] if n is None else n
+    p = x.numel() // (n * c)
+    if out is None:
+        out = torch.empty_like(x)
+    ws = _gn_workspace(x.device, n)
+    rc = _l.load().vgen_group_norm(_p(x), _p(out), n, p, c, _p(gamma), _p(beta), float(eps), 1 if silu else 0,
+                                   _p(ws), _stream())
+    _l.check(rc, "vgen_group_norm")
+    return out
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, out=None):
+    _chk16(x, "x")
+    x2, ldx = _rows_view(x, "x")
+    rows, c = x2.shape
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    o2, ldo = _rows_view(out, "out")
+    rc = _l.load().vgen_layer_norm(_p(x2), _p(o2), rows, c, ldx, ldo, _p(gamma), _p(beta), float(eps), _stream())
+    _l.check(rc, "vgen_layer_norm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+def attention_d64(q, k, v, heads, kv_batch_div=1, out=None):
+    """q [b, lq, heads*64] (last-dim-contiguous views allowed, e.g. slices of a fused qkv buffer),
+    k/v [b // kv_batch_div, lk, heads*64] -> out [b, lq, heads*64]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk16(t, nm)
+        if t.dim() != 3 or t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise _l.VgenError(f"attention_d64: {nm} must be [b, l, h*64] with dense batch stride")
+    b, lq, inner = q.shape
+    lk = k.shape[1]
+    if inner != heads * 64 or k.shape[2] != inner or v.shape != k.shape or k.shape[0] * kv_batch_div != b:
+        raise _l.VgenError("attention_d64: shape mismatch")
+    if out is None:
+        out = torch.empty(b, lq, inner, device=q.device, dtype=torch.float16)
+    rc = _l.load().vgen_attention_d64(_p(q), _p(k), _p(v), _p(out), b, heads, lq, lk, q.stride(1), k.stride(1),
+                                      v.stride(1), out.stride(1), kv_batch_div, 64 ** -0.5, _stream())
+    _l.check(rc, "vgen_attention_d64")
+    return out
+
+
+def attention_temporal(q, k, v, heads, head_dim, out=None):
+    """q/k/v [f, npix, heads*head_dim] views (frame-major): attention over the f tokens of each pixel."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk16(t, nm)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise _l.VgenError(f"attention_temporal: {nm} must be [f, npix, c] with contiguous channels")
+    f, npix, inner = q.shape
+    if inner != heads * head_dim or k.shape != q.shape or v.shape != q.shape:
+        raise _l.VgenError("attention_temporal: shape mismatch")
+    if k.stride() != q.stride() or v.stride() != q.stride():
+        raise _l.VgenError("attention_temporal: q/k/v must share strides")
+    if out is None:
+        out = torch.empty(f, npix, inner, device=q.device, dtype=torch.float16)
+    rc = _l.load().vgen_attention_temporal(_p(q), _p(k), _p(v), _p(out), npix, heads, f, head_dim, q.stride(0), q.stride(1),
+                                           out.stride(0), out.stride(1), head_dim ** -0.5, _stream())
+    _l.check(rc, "vgen_attention_temporal")
+    return out
+
+
+def softmax_rows_(x, scale=1.0):
+    _chk16(x, "x")
+    x2, ld = _rows_view(x, "x")
+    rc = _l.load().vgen_softmax_rows(_p(x2), x2.shape[0], x2.shape[1], ld, float(scale), _stream())
+    _l.check(rc, "vgen_softmax_rows")
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# data movement / pointwise
+def cp_to_pc(x, n, c, p, c_pad=None):
+    """x viewed as [n, c, p] (fp32 or fp16, contiguous) -> [n, p, c_pad] fp16."""
+    c_pad = c if c_pad is None else c_pad
+    if not x.is_contiguous() or x.dtype not in (torch.float32, torch.float16):
+        raise _l.VgenError("cp_to_pc: x must be contiguous fp32/fp16")
+    y = torch.empty(n, p, c_pad, device=x.device, dtype=torch.float16)
+    rc = _l.load().vgen_cp_to_pc(_p(x), 1 if x.dtype == torch.float32 else 0, _p(y), n, c, p, c_pad, _stream())
+    _l.check(rc, "vgen_cp_to_pc")
+    return y
+
+
+def pc_to_cp(x, n, c, p, out_dtype=torch.float16):
+    """x [n, p, ld>=c] fp16 -> [n, c, p]."""
+    _chk16(x, "x")
+    ldx = x.shape[-1]
+    y = torch.empty(n, c, p, device=x.device, dtype=out_dtype)
+    rc = _l.load().vgen_pc_to_cp(_p(x), ldx, _p(y), 1 if out_dtype == torch.float32 else 0, n, c, p, _stream())
+    _l.check(rc, "vgen_pc_to_cp")
+    return y
+
+
+def im2col(x, kh, kw, stride, pad_t, pad_l, ho, wo, kpad, act_silu=False):
+    _chk16(x, "x")
+    nimg, h, w, c = x.shape
+    out = torch.empty(nimg * ho * wo, kpad, device=x.device, dtype=torch.float16)
+    rc = _l.load().vgen_im2col(_p(x), _p(out), nimg, h, w, c, kh, kw, stride, pad_t, pad_l, ho, wo, kpad,
+                               1 if act_silu else 0, _stream())
+    _l.check(rc, "vgen_im2col")
+    return out
+
+
+def upsample_nearest2x(x):
+    _chk16(x, "x")
+    nimg, h, w, c = x.shape
+    y = torch.empty(nimg, 2 * h, 2 * w, c, device=x.device, dtype=torch.float16)
+    rc = _l.load().vgen_upsample_nearest2x(_p(x), _p(y), nimg, h, w, c, _stream())
+    _l.check(rc, "vgen_upsample_nearest2x")
+    return y
+
+
+def copy2d(src, dst):
+    """dst[r, :cols] = src[r, :cols] for 2-D row views."""
+    s2, lds = _rows_view(src, "src")
+    d2, ldd = _rows_view(dst, "dst")
+    if s2.shape != d2.shape:
+        raise _l.VgenError("copy2d: shape mismatch")
+    rc = _l.load().vgen_copy2d(_p(s2), lds, _p(d2), ldd, s2.shape[0], s2.shape[1], _stream())
+    _l.check(rc, "vgen_copy2d")
+    return dst
+
+
+def concat_channels(a, b):
+    """torch.cat([a, b], dim=-1) for channels-last tensors with equal leading dims."""
+    ca, cb = a.shape[-1], b.shape[-1]
+    out = torch.empty(*a.shape[:-1], ca + cb, device=a.device, dtype=torch.float16)
+    o2 = out.reshape(-1, ca + cb)
+    copy2d(a.reshape(-1, ca), o2[:, :ca])
+    copy2d(b.reshape(-1, cb), o2[:, ca:])
+    return out
+
+
+_ELT = {"silu": 0, "add": 1, "gelu": 2, "scale": 3, "axpy": 4}
+
+
+def eltwise(op, a, b=None, s=1.0, out=None):
+    _chk16(a, "a")
+    if out is None:
+        out = torch.empty_like(a)
+    rc = _l.load().vgen_eltwise(_ELT[op], _p(a), _p(b), _p(out), a.numel(), float(s), _stream())
+    _l.check(rc, "vgen_eltwise")
+    return out
+
+
+def linear_small(a, w, bias=None, residual=None, silu_in=False, gelu_out=False, out=None):
+    _chk16(a, "a"), _chk16(w, "w")
+    lead = a.shape[:-1]
+    a2, lda = _rows_view(a, "a")
+    m, k = a2.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty(*lead, n, device=a.device, dtype=torch.float16)
+    o2, ldo = _rows_view(out, "out")
+    r2, ldr = (None, 0) if residual is None else _rows_view(residual, "residual")
+    rc = _l.load().vgen_linear_small(_p(a2), m, k, lda, _p(w), _p(bias), n, _p(r2), ldr, _p(o2), ldo,
+                                     1 if silu_in else 0, 1 if gelu_out else 0, _stream())
+    _l.check(rc, "vgen_linear_small")
+    return out
+
+
+def sinusoidal_embedding(t, dim):
+    t32 = t.to(torch.float32).contiguous()
+    out = torch.empty(t32.numel(), dim, device=t.device, dtype=torch.float16)
+    rc = _l.load().vgen_sinusoidal_embedding(_p(t32), _p(out), t32.numel(), dim, _stream())
+    _l.check(rc, "vgen_sinusoidal_embedding")
+    return out
+
+
+def adaptive_avgpool(x, oh, ow, silu_in=False):
+    _chk16(x, "x")
+    nimg, h, w, c = x.shape
+    y = torch.empty(nimg, oh, ow, c, device=x.device, dtype=torch.float16)
+    rc = _l.load().vgen_adaptive_avgpool(_p(x), _p(y), nimg, h, w, c, oh, ow, 1 if silu_in else 0, _stream())
+    _l.check(rc, "vgen_adaptive_avgpool")
+    return y
+
+
+def ddim_step_(xt, y, u, coef7, guide_scale, mean_type_v=True, noise=None):
+    """In-place fused CFG + DDIM update of the fp32 latent xt; y/u fp16 model outputs (same layout)."""
+    if xt.dtype != torch.float32 or not xt.is_contiguous():
+        raise _l.VgenError("ddim_step_: xt must be contiguous fp32")
+    _chk16(y, "y")
+    c = (ctypes.c_float * 7)(*[float(v) for v in coef7])
+    rc = _l.load().vgen_ddim_step(_p(xt), _p(y), _p(u), _p(noise), xt.numel(), float(guide_scale or 0.0), c,
+                                  1 if mean_type_v else 0, _stream())
+    _l.check(rc, "vgen_ddim_step")
+    return xt
