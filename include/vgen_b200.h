@@ -41,6 +41,7 @@ typedef struct vgen_epilogue {
   const float* bias;        /* [n] fp32 or NULL                                                       */
   const void* group_bias;   /* fp16 [groups][n] or NULL: per-frame bias, added after fp16 rounding     */
   int64_t group_bias_ld;    /*   (ResBlock "h + emb_out": tools/modules/unet/util.py:909-919)          */
+  int64_t group_bias_div;   /*   row = image_index / group_bias_div (frames per video); 0 or 1 = per image */
   const void* residual;     /* fp16 [rows][n] or NULL: added after fp16 rounding (skip / x_in adds)    */
   int64_t residual_ld;
   int geglu;                /* 1: out[rows][n/2] = value * gelu(gate); W rows interleaved per bn block */

@@ -1,0 +1,22 @@
+"""vgen_b200 -- B200-native (sm_100a) implementation of the VGen sampling hot path:
+DiffusionDDIM.ddim_sample_loop -> UNetSD_T2VBase / UNetSD_I2VGen forward -> AutoencoderKL.decode,
+exposed under the reference's MODEL / DIFFUSION / AUTO_ENCODER registry names (`register()`).
+
+Every op of the path is a hand-written CUDA kernel in libvgen_b200.so (include/vgen_b200.h); this
+package holds only the host-side mirror of the reference interface.  There is no CPU / PyTorch
+fallback: without the built library or a CUDA device the forward raises.
+"""
+from .registry import register  # noqa: F401
+
+
+def __getattr__(name):  # lazy: importing the package must not require torch.cuda
+    if name in ("UNetSD_T2VBase", "UNetSD_I2VGen"):
+        from . import unet
+        return getattr(unet, name)
+    if name == "AutoencoderKL":
+        from .autoencoder import AutoencoderKL
+        return AutoencoderKL
+    if name == "DiffusionDDIM":
+        from .diffusion import DiffusionDDIM
+        return DiffusionDDIM
+    raise AttributeError(name)

@@ -1,0 +1,157 @@
+"""B200-native AutoencoderKL (SD-2.1 VAE): same constructor, state_dict keys and methods as the
+reference class (tools/modules/autoencoder.py:30-103); `decode` is a channels-last graph of
+libvgen_b200.so kernels (tcgen05 conv3x3 / 1x1, fused GroupNorm+SiLU, GEMM-based mid attention).
+
+The reference runs the decoder in fp32 (outside its autocast block, inference_i2vgen_entrance.py:224-230);
+here activations are fp16 with fp32 accumulation and fp32 norm/softmax statistics, and the result is
+returned as fp32 like the reference.  `encode_firsr_stage` is a conditioning-side call (SURVEY.md
+section 8f rank 2) and is not implemented in this round: it raises instead of falling back.
+"""
+from __future__ import annotations
+
+import collections
+
+import torch
+
+from . import arch, ops
+from .params import SpecModule
+from .unet import _f16, _f32, _pack_conv3x3
+
+
+class AutoencoderKL(SpecModule):
+    def __init__(self, ddconfig, embed_dim, pretrained=None, ignore_keys=[], image_key="image", colorize_nlabels=None,
+                 monitor=None, ema_decay=None, learn_logvar=False, use_vid_decoder=False, **kwargs):
+        super().__init__()
+        assert ddconfig["double_z"]
+        self.plan = arch.vae_plan(dict(ddconfig), embed_dim)
+        self.embed_dim = embed_dim
+        self.image_key = image_key
+        self.learn_logvar = learn_logvar
+        self._build_params(arch.vae_spec(self.plan))
+        if pretrained is not None:
+            self.init_from_ckpt(pretrained, ignore_keys=ignore_keys)
+
+    def init_from_ckpt(self, path, ignore_keys=list()):
+        """autoencoder.py:64-73: keys containing 'first_stage_model.' of an SD checkpoint, strict."""
+        sd = torch.load(path, map_location="cpu")["state_dict"]
+        new = collections.OrderedDict()
+        for k in list(sd.keys()):
+            if k.find("first_stage_model") >= 0:
+                new[k.split("first_stage_model.")[-1]] = sd[k]
+        self.load_state_dict(new, strict=True)
+
+    # ------------------------------------------------------------------------------ packing
+    def _pack(self):
+        sd = self.state_dict()
+        dev = self.device
+        if dev.type != "cuda":
+            raise ops._l.VgenError("vgen_b200 AutoencoderKL.decode needs the module on a CUDA device (no CPU path exists)")
+        W = {}
+
+        def norm(p):
+            W[p + "g"], W[p + "b"] = _f32(sd[p + "weight"], dev), _f32(sd[p + "bias"], dev)
+
+        def conv3(p, cin_pad=None):
+            W[p + "w"], W[p + "b"] = _pack_conv3x3(sd[p + "weight"], dev, cin_pad), _f32(sd[p + "bias"], dev)
+
+        def conv1(p):
+            w = sd[p + "weight"]
+            W[p + "w"], W[p + "b"] = _f16(w.reshape(w.shape[0], -1), dev), _f32(sd[p + "bias"], dev)
+
+        def resnet(p):
+            norm(p + "norm1."), conv3(p + "conv1."), norm(p + "norm2."), conv3(p + "conv2.")
+            if (p + "nin_shortcut.weight") in sd:
+                conv1(p + "nin_shortcut.")
+
+        conv1("post_quant_conv.")
+        conv3("decoder.conv_in.", cin_pad=8)
+        resnet("decoder.mid.block_1."), resnet("decoder.mid.block_2.")
+        a = "decoder.mid.attn_1."
+        norm(a + "norm.")
+        for nm in ("q.", "k.", "v.", "proj_out."):
+            conv1(a + nm)
+        for lvl in range(len(self.plan.ch_mult)):
+            for j in range(self.plan.num_res_blocks + 1):
+                resnet(f"decoder.up.{lvl}.block.{j}.")
+            if lvl != 0:
+                conv3(f"decoder.up.{lvl}.upsample.conv.")
+        norm("decoder.norm_out."), conv3("decoder.conv_out.")
+        self._packed = W
+        return W
+
+    # ------------------------------------------------------------------------------ blocks
+    @staticmethod
+    def _conv3(x, W, p, residual=None):
+        n, h, w, c = x.shape
+        wt = W[p + "w"]
+        if c % 64 == 0 and wt.shape[1] == 9 * c:
+            return ops.conv2d_3x3(x, wt, bias=W[p + "b"], residual=residual)
+        col = ops.im2col(x, 3, 3, 1, 1, 1, h, w, wt.shape[1])
+        return ops.linear(col, wt, bias=W[p + "b"], residual=residual).view(n, h, w, wt.shape[0])
+
+    def _resnet(self, x, W, p):
+        """ResnetBlock.forward, autoencoder.py:315-335 (temb None)."""
+        n, h, w, cin = x.shape
+        g = ops.group_norm(x, W[p + "norm1.g"], W[p + "norm1.b"], 1e-6, True)
+        hcur = self._conv3(g, W, p + "conv1.")
+        g = ops.group_norm(hcur, W[p + "norm2.g"], W[p + "norm2.b"], 1e-6, True)
+        if (p + "nin_shortcut.w") in W:
+            skip = ops.linear(x.view(-1, cin), W[p + "nin_shortcut.w"], bias=W[p + "nin_shortcut.b"])
+        else:
+            skip = x.view(-1, cin)
+        return self._conv3(g, W, p + "conv2.", residual=skip)
+
+    def _attn(self, x, W, p):
+        """AttnBlock.forward, autoencoder.py:365-389: single-head attention over h*w tokens of width c.
+        Done as three GEMMs + a row softmax per image: S = q k^T / sqrt(c), P = softmax(S), O = P v.
+        v's bias is added after P v (rows of P sum to 1), so v^T can be produced directly as W_v g^T."""
+        n, h, w, c = x.shape
+        hw = h * w
+        g = ops.group_norm(x, W[p + "norm.g"], W[p + "norm.b"], 1e-6, False).view(n, hw, c)
+        q = ops.linear(g, W[p + "q.w"], bias=W[p + "q.b"])
+        k = ops.linear(g, W[p + "k.w"], bias=W[p + "k.b"])
+        o = torch.empty(n, hw, c, device=x.device, dtype=torch.float16)
+        for i in range(n):
+            vt = ops.linear(W[p + "v.w"], g[i])                                # [c, hw] = W_v g^T
+            s = ops.linear(q[i], k[i], alpha=float(c) ** -0.5)                 # [hw, hw]
+            ops.softmax_rows_(s, 1.0)
+            ops.linear(s, vt, bias=W[p + "v.b"], out=o[i])                     # [hw, c]
+        out = ops.linear(o.view(-1, c), W[p + "proj_out.w"], bias=W[p + "proj_out.b"], residual=x.view(-1, c))
+        return out.view(n, h, w, c)
+
+    # ------------------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def decode(self, z, **kwargs):
+        """autoencoder.py:100-103 -> Decoder.forward :653-686.  z [n, 4, h, w] -> fp32 [n, 3, 8h, 8w]."""
+        if not z.is_cuda:
+            raise ops._l.VgenError("vgen_b200 AutoencoderKL.decode: z must be a CUDA tensor (no CPU path exists)")
+        W = self._packed or self._pack()
+        n, zc, h, w = z.shape
+        x = ops.cp_to_pc(z.contiguous(), n, zc, h * w)                                    # [n, hw, zc]
+        x = ops.linear_small(x.view(-1, zc), W["post_quant_conv.w"], W["post_quant_conv.b"])
+        x8 = torch.zeros(n * h * w, 8, device=z.device, dtype=torch.float16)
+        ops.copy2d(x, x8[:, :zc])
+        d = "decoder."
+        hcur = self._conv3(x8.view(n, h, w, 8), W, d + "conv_in.")
+        hcur = self._resnet(hcur, W, d + "mid.block_1.")
+        hcur = self._attn(hcur, W, d + "mid.attn_1.")
+        hcur = self._resnet(hcur, W, d + "mid.block_2.")
+        for lvl in reversed(range(len(self.plan.ch_mult))):
+            for j in range(self.plan.num_res_blocks + 1):
+                hcur = self._resnet(hcur, W, f"{d}up.{lvl}.block.{j}.")
+            if lvl != 0:
+                hcur = self._conv3(ops.upsample_nearest2x(hcur), W, f"{d}up.{lvl}.upsample.conv.")
+        g = ops.group_norm(hcur, W[d + "norm_out.g"], W[d + "norm_out.b"], 1e-6, True)
+        out = self._conv3(g, W, d + "conv_out.")                                          # [n, H, W, 3]
+        nn_, hh, ww, oc = out.shape
+        return ops.pc_to_cp(out.view(nn_, hh * ww, oc), nn_, oc, hh * ww, torch.float32).view(nn_, oc, hh, ww)
+
+    def encode_firsr_stage(self, x, scale_factor=1.0):
+        raise NotImplementedError("vgen_b200: AutoencoderKL.encode_firsr_stage is conditioning-side (next-round scope); "
+                                  "use the reference encoder for conditioning latents")
+
+    def encode(self, x):
+        raise NotImplementedError("vgen_b200: AutoencoderKL.encode is out of the sampling hot path this round")
+
+    def forward(self, input, sample_posterior=True):
+        raise NotImplementedError("vgen_b200: AutoencoderKL.forward (training) is out of scope")

@@ -56,6 +56,7 @@ static int fill_epilogue(TapGemmArgs* t, void* out, long ldo, const vgen_epilogu
   e.bias = epi ? epi->bias : nullptr;
   e.group_bias = epi ? reinterpret_cast<const __half*>(epi->group_bias) : nullptr;
   e.ld_group_bias = epi ? epi->group_bias_ld : 0;
+  e.group_bias_div = (epi && epi->group_bias_div > 1) ? (int)epi->group_bias_div : 1;
   e.residual = epi ? reinterpret_cast<const __half*>(epi->residual) : nullptr;
   e.ldr = epi ? epi->residual_ld : 0;
   e.geglu = epi ? epi->geglu : 0;

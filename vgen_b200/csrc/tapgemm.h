@@ -28,6 +28,7 @@ struct TapGemmEpilogue {
   const float* bias;         // [n] or null   (GEGLU: indexed like the packed W rows)
   const __half* group_bias;  // [d3][n] or null: added per outermost coordinate (frame) after rounding
   long ld_group_bias;
+  int group_bias_div;        // bias row = i3 / group_bias_div
   const __half* residual;    // [rows][n] or null: added after rounding
   long ldr;
   int geglu;                 // out has n/2 columns: value * gelu(gate)

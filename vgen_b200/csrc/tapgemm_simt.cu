@@ -38,7 +38,7 @@ __global__ void tapgemm_simt_kernel(const __half* __restrict__ A, long st1, long
   if (!e.geglu) {
     a = dot(n) * e.alpha;
     if (e.bias) a += e.bias[n];
-    if (e.group_bias) a = __half2float(__float2half_rn(a)) + __half2float(e.group_bias[(long)i3 * e.ld_group_bias + n]);
+    if (e.group_bias) a = __half2float(__float2half_rn(a)) + __half2float(e.group_bias[(long)(i3 / e.group_bias_div) * e.ld_group_bias + n]);
     if (e.residual) a = __half2float(__float2half_rn(a)) + __half2float(e.residual[row * e.ldr + n]);
   } else {
     const int hb = s.bn / 2;

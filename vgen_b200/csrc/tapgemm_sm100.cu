@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
         const int n0 = nb_i * BN;
         __half* orow = e.out + row * e.ldo;
         const __half* rrow = e.residual ? e.residual + row * e.ldr : nullptr;
-        const __half* grow = e.group_bias ? e.group_bias + (long)i3 * e.ld_group_bias : nullptr;
+        const __half* grow = e.group_bias ? e.group_bias + (long)(i3 / e.group_bias_div) * e.ld_group_bias : nullptr;
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_row + c0, v);

@@ -24,6 +24,7 @@ class Epilogue(ctypes.Structure):
         ("bias", ctypes.c_void_p),
         ("group_bias", ctypes.c_void_p),
         ("group_bias_ld", ctypes.c_int64),
+        ("group_bias_div", ctypes.c_int64),
         ("residual", ctypes.c_void_p),
         ("residual_ld", ctypes.c_int64),
         ("geglu", ctypes.c_int),

@@ -37,7 +37,7 @@ def _rows_view(t, name):
     return t2, t2.stride(0)
 
 
-def _epilogue(n_out, bias=None, group_bias=None, residual=None, alpha=1.0, geglu=False, bn=0):
+def _epilogue(n_out, bias=None, group_bias=None, residual=None, alpha=1.0, geglu=False, bn=0, group_div=1):
     e = Epilogue()
     e.alpha = float(alpha)
     keep = []
@@ -50,6 +50,7 @@ def _epilogue(n_out, bias=None, group_bias=None, residual=None, alpha=1.0, geglu
         _chk16(group_bias, "group_bias")
         e.group_bias = group_bias.data_ptr()
         e.group_bias_ld = group_bias.stride(0)
+        e.group_bias_div = int(group_div)
         keep.append(group_bias)
     if residual is not None:
         _chk16(residual, "residual")
@@ -83,7 +84,7 @@ def linear(a, w, bias=None, residual=None, alpha=1.0, geglu=False, out=None, bn=
     return out
 
 
-def conv2d_3x3(x, w, bias=None, group_bias=None, residual=None, out=None, bn=0):
+def conv2d_3x3(x, w, bias=None, group_bias=None, residual=None, out=None, bn=0, group_div=1):
     """x [nimg, h, w, c] fp16 -> [nimg, h, w, n]; w [n, 9*c] with k = (ky*3+kx)*c + ci."""
     _chk16(x, "x"), _chk16(w, "w")
     if not x.is_contiguous() or x.dim() != 4:
@@ -95,7 +96,7 @@ def conv2d_3x3(x, w, bias=None, group_bias=None, residual=None, out=None, bn=0):
     if out is None:
         out = torch.empty(nimg, h, wd, n, device=x.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
-    e, keep = _epilogue(n, bias, group_bias, residual, 1.0, False, bn)
+    e, keep = _epilogue(n, bias, group_bias, residual, 1.0, False, bn, group_div)
     rc = _l.load().vgen_conv2d_3x3(_p(x), nimg, h, wd, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream())
     _l.check(rc, "vgen_conv2d_3x3")
     return out

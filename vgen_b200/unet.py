@@ -1,0 +1,445 @@
+"""B200-native UNetSD_T2VBase / UNetSD_I2VGen: same constructor arguments, state_dict keys and
+forward signature as the reference classes (tools/modules/unet/unet_t2v.py:19-277,
+unet_i2vgen.py:19-346), but the forward is a fixed-layout graph of libvgen_b200.so kernels.
+
+Design (not a port of the reference's module tree):
+  * activations stay fp16 channels-last [(b f), h, w, C] for the whole forward; the reference's dozens
+    of '(b f) c h w <-> b c f h w' / '(b h w) f c' permute+contiguous copies (unet_t2v.py:294-296,
+    util.py:1251-1280,923-926) do not exist: temporal kernels address frames by stride.
+  * weights are repacked once per load into GEMM-ready fp16 [out][taps*in] matrices; q/k/v projections
+    are fused into one GEMM; GEGLU value/gate rows are interleaved for the fused epilogue; the cross
+    attention K/V of the (frame-invariant) context are computed once per video, not once per frame.
+  * bias, timestep-embedding add, residual adds and GEGLU run in the GEMM epilogues.
+Numerics follow the reference under fp16 autocast: fp16 operands, fp32 accumulation and fp32
+norm/softmax statistics, fp16 rounding where the reference materialises an fp16 tensor.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import arch, ops
+from .params import SpecModule
+
+
+def _f16(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float16).contiguous()
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _pack_conv3x3(w, dev, cin_pad=None):
+    """[n, c, 3, 3] -> [n, 9*c'] with k = (ky*3+kx)*c' + ci (c' = c or the padded channel count),
+    K padded with zeros to a multiple of 64 for the tap-GEMM."""
+    n, c = w.shape[0], w.shape[1]
+    cp = cin_pad or c
+    wp = torch.zeros(n, 3, 3, cp, dtype=torch.float32)
+    wp[..., :c] = w.detach().float().cpu().permute(0, 2, 3, 1)
+    wp = wp.reshape(n, 9 * cp)
+    kpad = ((9 * cp + 63) // 64) * 64
+    if kpad != 9 * cp:
+        wp = torch.cat([wp, torch.zeros(n, kpad - 9 * cp)], dim=1)
+    return wp.to(device=dev, dtype=torch.float16).contiguous()
+
+
+def _geglu_bn(n):
+    for bn in (256, 192, 128, 64):
+        if n % bn == 0:
+            return bn
+    raise ValueError(f"GEGLU width {n} is not a multiple of 64")
+
+
+class _Weights:
+    """Device-side packed weights of one model (built by _pack)."""
+
+    def __init__(self):
+        self.t = {}
+
+
+class _UNetBase(SpecModule):
+    KIND = "t2v"
+
+    def __init__(self, config=None, in_dim=4, dim=512, y_dim=512, context_dim=512, hist_dim=156, dim_condition=4,
+                 out_dim=6, num_tokens=4, dim_mult=[1, 2, 3, 4], num_heads=None, head_dim=64, num_res_blocks=3,
+                 attn_scales=[1 / 2, 1 / 4, 1 / 8], use_scale_shift_norm=True, dropout=0.1, temporal_attn_times=1,
+                 temporal_attention=True, use_checkpoint=False, use_image_dataset=False, use_sim_mask=False,
+                 training=True, inpainting=True, use_fps_condition=False, p_all_zero=0.1, p_all_keep=0.1, zero_y=None,
+                 adapter_transformer_layers=1, concat_dim=8, **kwargs):
+        super().__init__()
+        if head_dim != 64:
+            raise NotImplementedError("vgen_b200: head_dim must be 64 (all released VGen checkpoints)")
+        if use_image_dataset:
+            raise NotImplementedError("vgen_b200: use_image_dataset (training-time flag) is not supported")
+        if adapter_transformer_layers != 1:
+            raise NotImplementedError("vgen_b200: adapter_transformer_layers != 1 is not supported")
+        self.plan = arch.unet_plan(self.KIND, in_dim=in_dim, dim=dim, y_dim=y_dim, context_dim=context_dim, out_dim=out_dim,
+                                   num_tokens=num_tokens, dim_mult=tuple(dim_mult), num_heads=num_heads, head_dim=head_dim,
+                                   num_res_blocks=num_res_blocks, attn_scales=tuple(attn_scales),
+                                   temporal_attention=temporal_attention, use_fps_condition=use_fps_condition,
+                                   concat_dim=concat_dim)
+        # attributes the reference exposes and engines read
+        self.in_dim, self.dim, self.y_dim, self.context_dim, self.out_dim = in_dim, dim, y_dim, context_dim, out_dim
+        self.embed_dim, self.num_tokens, self.head_dim = dim * 4, num_tokens, head_dim
+        self.zero_y = zero_y
+        self.use_fps_condition = self.plan.use_fps_condition
+        self._build_params(arch.unet_spec(self.plan), arch.unet_zero_init)
+
+    # ------------------------------------------------------------------------------ weight packing
+    def _pack(self):
+        sd = {k: v for k, v in self.state_dict().items()}
+        dev = self.device
+        if dev.type != "cuda":
+            raise ops._l.VgenError("vgen_b200 UNet forward needs the module on a CUDA device (no CPU path exists)")
+        W = {}
+
+        def lin(p, bias=True):
+            w = sd[p + "weight"]
+            W[p + "w"] = _f16(w.reshape(w.shape[0], -1), dev)
+            if bias:
+                W[p + "b"] = _f32(sd[p + "bias"], dev)
+
+        def norm(p):
+            W[p + "g"] = _f32(sd[p + "weight"], dev)
+            W[p + "b"] = _f32(sd[p + "bias"], dev)
+
+        def conv3(p, cin_pad=None):
+            W[p + "w"] = _pack_conv3x3(sd[p + "weight"], dev, cin_pad)
+            W[p + "b"] = _f32(sd[p + "bias"], dev)
+
+        def tconv(p):
+            w = sd[p + "weight"]  # [n, c, 3, 1, 1] -> [n, 3*c], k = kt*c + ci
+            W[p + "w"] = _f16(w[:, :, :, 0, 0].permute(0, 2, 1).reshape(w.shape[0], -1), dev)
+            W[p + "b"] = _f32(sd[p + "bias"], dev)
+
+        def block(p, cross):
+            a1, a2 = p + "attn1.", p + "attn2."
+            W[a1 + "qkv"] = _f16(torch.cat([sd[a1 + "to_q.weight"], sd[a1 + "to_k.weight"], sd[a1 + "to_v.weight"]], 0), dev)
+            lin(a1 + "to_out.0.")
+            if cross:
+                W[a2 + "q"] = _f16(sd[a2 + "to_q.weight"], dev)
+                W[a2 + "kv"] = _f16(torch.cat([sd[a2 + "to_k.weight"], sd[a2 + "to_v.weight"]], 0), dev)
+            else:
+                W[a2 + "qkv"] = _f16(torch.cat([sd[a2 + "to_q.weight"], sd[a2 + "to_k.weight"], sd[a2 + "to_v.weight"]], 0), dev)
+            lin(a2 + "to_out.0.")
+            for nm in ("norm1.", "norm2.", "norm3."):
+                norm(p + nm)
+            gw, gb = sd[p + "ff.net.0.proj.weight"], sd[p + "ff.net.0.proj.bias"]
+            bn = _geglu_bn(gw.shape[0])
+            wp, bp = ops.pack_geglu_weight(gw.detach().float(), gb.detach().float(), bn)
+            W[p + "ff.geglu.w"], W[p + "ff.geglu.b"], W[p + "ff.geglu.bn"] = _f16(wp, dev), _f32(bp, dev), bn
+            lin(p + "ff.net.2.")
+
+        def layer(L):
+            p = L.prefix
+            if L.kind == "conv_in":
+                conv3(p, cin_pad=8 if L.cin < 8 else None)
+            elif L.kind == "res":
+                norm(p + "in_layers.0."), conv3(p + "in_layers.2.")
+                lin(p + "emb_layers.1.")
+                norm(p + "out_layers.0."), conv3(p + "out_layers.3.")
+                if L.cin != L.cout:
+                    lin(p + "skip_connection.")
+                for name, widx in (("conv1", 2), ("conv2", 3), ("conv3", 3), ("conv4", 3)):
+                    q = f"{p}temopral_conv.{name}."
+                    norm(q + "0."), tconv(f"{q}{widx}.")
+            elif L.kind == "spatial":
+                norm(p + "norm."), lin(p + "proj_in."), block(p + "transformer_blocks.0.", True), lin(p + "proj_out.")
+            elif L.kind == "temporal":
+                norm(p + "norm."), lin(p + "proj_in."), block(p + "transformer_blocks.0.", False), lin(p + "proj_out.")
+            elif L.kind == "down":
+                conv3(p + "op.")
+            elif L.kind == "up":
+                conv3(p + "conv.")
+
+        for pre in ("time_embed.0.", "time_embed.2."):
+            lin(pre)
+        if self.plan.use_fps_condition:
+            lin("fps_embedding.0."), lin("fps_embedding.2.")
+        if self.KIND == "i2vgen":
+            lin("context_embedding.0."), lin("context_embedding.2.")
+            conv3("local_image_concat.0.", cin_pad=8), conv3("local_image_concat.2."), conv3("local_image_concat.4.")
+            e = "local_temporal_encoder.layers.0."
+            norm(e + "0.norm."), lin(e + "0.fn.to_qkv.", bias=False), lin(e + "0.fn.to_out.0.")
+            lin(e + "1.net.0.0."), lin(e + "1.net.2.")
+            conv3("local_image_embedding.0.", cin_pad=8), conv3("local_image_embedding.3."), conv3("local_image_embedding.5.")
+        for blk in self.plan.input_blocks:
+            for L in blk:
+                layer(L)
+        for L in self.plan.middle:
+            layer(L)
+        for blk in self.plan.output_blocks:
+            for L in blk:
+                layer(L)
+        norm("out.0."), conv3("out.2.")
+        self._packed = W
+        return W
+
+    # ------------------------------------------------------------------------------ building blocks
+    def _conv3x3_any(self, x, W, p, **epi):
+        """3x3 stride-1 conv: TMA tap-GEMM when C % 64 == 0, otherwise im2col + GEMM."""
+        n, h, w, c = x.shape
+        wt = W[p + "w"]
+        if c % 64 == 0 and wt.shape[1] == 9 * c:
+            return ops.conv2d_3x3(x, wt, bias=W[p + "b"], **epi)
+        col = ops.im2col(x, 3, 3, 1, 1, 1, h, w, wt.shape[1], act_silu=epi.pop("act_silu", False))
+        out = ops.linear(col, wt, bias=W[p + "b"], residual=epi.get("residual"))
+        return out.view(n, h, w, wt.shape[0])
+
+    def _conv3x3_s2(self, x, W, p, act_silu=False):
+        n, h, w, c = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        wt = W[p + "w"]
+        col = ops.im2col(x, 3, 3, 2, 1, 1, ho, wo, wt.shape[1], act_silu=act_silu)
+        return ops.linear(col, wt, bias=W[p + "b"]).view(n, ho, wo, wt.shape[0])
+
+    def _res_block(self, x, emb, L, W, b, f):
+        """ResBlock._forward + TemporalConvBlock_v2 (util.py:900-927,1686-1697)."""
+        p = L.prefix
+        n, h, w, _ = x.shape
+        e = ops.linear_small(emb, W[p + "emb_layers.1.w"], W[p + "emb_layers.1.b"], silu_in=True)  # [b, cout]
+        g = ops.group_norm(x, W[p + "in_layers.0.g"], W[p + "in_layers.0.b"], 1e-5, True)
+        hcur = ops.conv2d_3x3(g, W[p + "in_layers.2.w"], bias=W[p + "in_layers.2.b"], group_bias=e, group_div=f)
+        g = ops.group_norm(hcur, W[p + "out_layers.0.g"], W[p + "out_layers.0.b"], 1e-5, True)
+        if L.cin != L.cout:
+            skip = ops.linear(x.view(-1, L.cin), W[p + "skip_connection.w"], bias=W[p + "skip_connection.b"])
+        else:
+            skip = x
+        hcur = ops.conv2d_3x3(g, W[p + "out_layers.3.w"], bias=W[p + "out_layers.3.b"], residual=skip.view(-1, L.cout))
+        # temporal conv: GroupNorm statistics over all frames of a video, 3-tap conv over frames
+        t = hcur
+        names = (("conv1", 2), ("conv2", 3), ("conv3", 3), ("conv4", 3))
+        for i, (name, widx) in enumerate(names):
+            q = f"{p}temopral_conv.{name}."
+            g = ops.group_norm(t, W[q + "0.g"], W[q + "0.b"], 1e-5, True, n=b)
+            last = i == len(names) - 1
+            out = torch.empty_like(hcur)
+            for bi in range(b):
+                gv = g.view(b, f, h * w, L.cout)[bi]
+                rv = hcur.view(b, f, h * w, L.cout)[bi] if last else None
+                ops.tconv3(gv, W[f"{q}{widx}.w"], bias=W[f"{q}{widx}.b"], residual=rv, out=out.view(b, f, h * w, L.cout)[bi])
+            t = out
+        return t
+
+    def _self_attn_spatial(self, xn, W, p, heads, n, hw, inner):
+        qkv = ops.linear(xn, W[p + "qkv"])                      # [M, 3*inner]
+        v3 = qkv.view(n, hw, 3 * inner)
+        return ops.attention_d64(v3[:, :, :inner], v3[:, :, inner:2 * inner], v3[:, :, 2 * inner:], heads)
+
+    def _basic_block_spatial(self, t, ctx_tokens, W, p, heads, n, hw, inner, f):
+        """BasicTransformerBlock on tokens t [M, inner] (M = n*hw); ctx_tokens [b, L, ctx_dim] fp16."""
+        xn = ops.layer_norm(t, W[p + "norm1.g"], W[p + "norm1.b"])
+        a = self._self_attn_spatial(xn, W, p + "attn1.", heads, n, hw, inner)
+        t = ops.linear(a.view(-1, inner), W[p + "attn1.to_out.0.w"], bias=W[p + "attn1.to_out.0.b"], residual=t)
+        xn = ops.layer_norm(t, W[p + "norm2.g"], W[p + "norm2.b"])
+        q = ops.linear(xn, W[p + "attn2.q"]).view(n, hw, inner)
+        bctx, lctx, cdim = ctx_tokens.shape
+        kv = ops.linear(ctx_tokens.view(-1, cdim), W[p + "attn2.kv"]).view(bctx, lctx, 2 * inner)
+        a = ops.attention_d64(q, kv[:, :, :inner], kv[:, :, inner:], heads, kv_batch_div=f)
+        t = ops.linear(a.view(-1, inner), W[p + "attn2.to_out.0.w"], bias=W[p + "attn2.to_out.0.b"], residual=t)
+        return self._feed_forward(t, W, p)
+
+    def _feed_forward(self, t, W, p):
+        xn = ops.layer_norm(t, W[p + "norm3.g"], W[p + "norm3.b"])
+        gg = ops.linear(xn, W[p + "ff.geglu.w"], bias=W[p + "ff.geglu.b"], geglu=True, bn=W[p + "ff.geglu.bn"])
+        return ops.linear(gg, W[p + "ff.net.2.w"], bias=W[p + "ff.net.2.b"], residual=t)
+
+    def _spatial_transformer(self, x, ctx_tokens, L, W, f):
+        """SpatialTransformer.forward, use_linear=True (util.py:354-373)."""
+        p = L.prefix
+        n, h, w, c = x.shape
+        g = ops.group_norm(x, W[p + "norm.g"], W[p + "norm.b"], 1e-6, False)
+        t = ops.linear(g.view(-1, c), W[p + "proj_in.w"], bias=W[p + "proj_in.b"])
+        t = self._basic_block_spatial(t, ctx_tokens, W, p + "transformer_blocks.0.", L.heads, n, h * w, L.inner, f)
+        out = ops.linear(t, W[p + "proj_out.w"], bias=W[p + "proj_out.b"], residual=x.view(-1, c))
+        return out.view(n, h, w, c)
+
+    def _temporal_attn(self, xn, W, p, heads, b, f, hw, inner):
+        qkv = ops.linear(xn, W[p + "qkv"]).view(b, f, hw, 3 * inner)
+        out = torch.empty(b, f, hw, inner, device=xn.device, dtype=torch.float16)
+        for bi in range(b):
+            v = qkv[bi]
+            ops.attention_temporal(v[:, :, :inner], v[:, :, inner:2 * inner], v[:, :, 2 * inner:], heads, 64, out=out[bi])
+        return out
+
+    def _temporal_transformer(self, x, L, W, b, f):
+        """TemporalTransformer.forward, only_self_att=True (util.py:1240-1286): both attentions are
+        self-attention over the f frames of a pixel; GroupNorm statistics span all frames."""
+        p = L.prefix
+        n, h, w, c = x.shape
+        hw, inner = h * w, L.inner
+        g = ops.group_norm(x, W[p + "norm.g"], W[p + "norm.b"], 1e-6, False, n=b)
+        t = ops.linear(g.view(-1, c), W[p + "proj_in.w"], bias=W[p + "proj_in.b"])
+        q = p + "transformer_blocks.0."
+        for att, nrm in (("attn1.", "norm1."), ("attn2.", "norm2.")):
+            xn = ops.layer_norm(t, W[q + nrm + "g"], W[q + nrm + "b"])
+            a = self._temporal_attn(xn, W, q + att, L.heads, b, f, hw, inner)
+            t = ops.linear(a.view(-1, inner), W[q + att + "to_out.0.w"], bias=W[q + att + "to_out.0.b"], residual=t)
+        t = self._feed_forward(t, W, q)
+        out = ops.linear(t, W[p + "proj_out.w"], bias=W[p + "proj_out.b"], residual=x.view(-1, c))
+        return out.view(n, h, w, c)
+
+    def _run_layer(self, x, L, W, emb, ctx_tokens, b, f):
+        if L.kind == "res":
+            return self._res_block(x, emb, L, W, b, f)
+        if L.kind == "spatial":
+            return self._spatial_transformer(x, ctx_tokens, L, W, f)
+        if L.kind == "temporal":
+            return self._temporal_transformer(x, L, W, b, f)
+        if L.kind == "down":
+            return self._conv3x3_s2(x, W, L.prefix + "op.")
+        if L.kind == "up":
+            return ops.conv2d_3x3(ops.upsample_nearest2x(x), W[L.prefix + "conv.w"], bias=W[L.prefix + "conv.b"])
+        if L.kind == "conv_in":
+            return self._conv3x3_any(x, W, L.prefix)
+        raise ValueError(L.kind)
+
+    def _trunk(self, x, emb, ctx_tokens, W, b, f):
+        """encoder / middle / decoder with skip concatenation + head (unet_t2v.py:257-277)."""
+        skips = []
+        for blk in self.plan.input_blocks:
+            for L in blk:
+                x = self._run_layer(x, L, W, emb, ctx_tokens, b, f)
+            skips.append(x)
+        for L in self.plan.middle:
+            x = self._run_layer(x, L, W, emb, ctx_tokens, b, f)
+        for blk in self.plan.output_blocks:
+            x = ops.concat_channels(x, skips.pop())
+            for L in blk:
+                x = self._run_layer(x, L, W, emb, ctx_tokens, b, f)
+        g = ops.group_norm(x, W["out.0.g"], W["out.0.b"], 1e-5, True)
+        return ops.conv2d_3x3(g, W["out.2.w"], bias=W["out.2.b"])
+
+    def _mlp(self, x, W, p):
+        h = ops.linear_small(x, W[p + "0.w"], W[p + "0.b"])
+        return ops.linear_small(h, W[p + "2.w"], W[p + "2.b"], silu_in=True)
+
+    def _time_embedding(self, t, fps, W):
+        emb = self._mlp(ops.sinusoidal_embedding(t, self.dim), W, "time_embed.")
+        if self.plan.use_fps_condition and fps is not None:
+            emb = ops.eltwise("add", emb, self._mlp(ops.sinusoidal_embedding(fps, self.dim), W, "fps_embedding."))
+        return emb
+
+    @staticmethod
+    def _to_f16_rows(t):
+        """[b, L, C] (fp32 or fp16) -> contiguous fp16 [b, L, C] through the cast kernel."""
+        b, L, c = t.shape
+        if t.dtype == torch.float16 and t.is_contiguous():
+            return t
+        return ops.cp_to_pc(t.contiguous().view(b * L, c, 1).float(), b * L, c, 1).view(b, L, c)
+
+    def _check_x(self, x, t):
+        if not x.is_cuda:
+            raise ops._l.VgenError("vgen_b200 UNet: inputs must be CUDA tensors (no CPU path exists)")
+        if x.dim() != 5:
+            raise ValueError("x must be [b, c, f, h, w]")
+        if t.numel() != x.shape[0]:
+            raise ValueError("t must have one entry per batch element")
+
+
+class UNetSD_T2VBase(_UNetBase):
+    """Drop-in for tools/modules/unet/unet_t2v.py:19-20 (registered as MODEL 'UNetSD_T2VBase')."""
+    KIND = "t2v"
+
+    @torch.no_grad()
+    def forward(self, x, t, y=None, fps=None, masked=None, video_mask=None, focus_present_mask=None,
+                prob_focus_present=0., mask_last_frame_num=0, **kwargs):
+        self._check_x(x, t)
+        W = self._packed or self._pack()
+        b, c, f, h, w = x.shape
+        emb = self._time_embedding(t, fps, W)
+        if y is None:
+            if self.zero_y is None:
+                raise ValueError("y is None and no zero_y was given")
+            y = self.zero_y.to(x.device).repeat(b, 1, 1)[:, :1, :]
+        ctx = self._to_f16_rows(y)
+        xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=8).view(b * f, h, w, 8)
+        out = self._trunk(xin, emb, ctx, W, b, f)                     # [(b f), h, w, out_dim]
+        return ops.pc_to_cp(out.view(b, f * h * w, self.out_dim), b, self.out_dim, f * h * w).view(b, self.out_dim, f, h, w)
+
+
+class UNetSD_I2VGen(_UNetBase):
+    """Drop-in for tools/modules/unet/unet_i2vgen.py:19-20 (registered as MODEL 'UNetSD_I2VGen')."""
+    KIND = "i2vgen"
+
+    def _small_conv(self, x, W, p, stride=1, act_silu=False):
+        n, h, w, c = x.shape
+        if stride == 2:
+            return self._conv3x3_s2(x, W, p, act_silu=act_silu)
+        wt = W[p + "w"]
+        col = ops.im2col(x, 3, 3, 1, 1, 1, h, w, wt.shape[1], act_silu=act_silu)
+        return ops.linear(col, wt, bias=W[p + "b"]).view(n, h, w, wt.shape[0])
+
+    def _local_concat(self, local_first, W, b, f, h, w):
+        """[Concat] branch, unet_i2vgen.py:281-295.  local_first: [b, 4, 1, h, w] (first-frame latent)."""
+        dev = local_first.device
+        if f > 1:
+            pos = (torch.arange(1, f, device=dev, dtype=torch.float32) / (f - 1)).view(1, 1, f - 1, 1, 1)
+            ximg = torch.cat([local_first.float(), pos.expand(b, local_first.shape[1], f - 1, h, w)], dim=2)
+        else:
+            ximg = local_first.float()
+        ximg = ops.cp_to_pc(ximg.contiguous(), b, ximg.shape[1], f * h * w, c_pad=8).view(b * f, h, w, 8)
+        ximg = self._small_conv(ximg, W, "local_image_concat.0.")
+        ximg = self._small_conv(ximg, W, "local_image_concat.2.", act_silu=True)
+        ximg = self._small_conv(ximg, W, "local_image_concat.4.", act_silu=True)      # [(b f), h, w, cd]
+        cd = ximg.shape[-1]
+        # TransformerV2(heads=2, dim=cd, dim_head=cd): tokens are the f frames of one pixel (util.py:1396-1452)
+        e = "local_temporal_encoder.layers.0."
+        tok = ximg.view(-1, cd)
+        xn = ops.layer_norm(tok, W[e + "0.norm.g"], W[e + "0.norm.b"])
+        qkv = ops.linear_small(xn, W[e + "0.fn.to_qkv.w"]).view(b, f, h * w, 6 * cd)
+        att = torch.empty(b, f, h * w, 2 * cd, device=dev, dtype=torch.float16)
+        for bi in range(b):
+            v = qkv[bi]
+            ops.attention_temporal(v[:, :, :2 * cd], v[:, :, 2 * cd:4 * cd], v[:, :, 4 * cd:], 2, cd, out=att[bi])
+        tok = ops.linear_small(att.view(-1, 2 * cd), W[e + "0.fn.to_out.0.w"], W[e + "0.fn.to_out.0.b"], residual=tok)
+        hid = ops.linear_small(tok, W[e + "1.net.0.0.w"], W[e + "1.net.0.0.b"], gelu_out=True)
+        tok = ops.linear_small(hid, W[e + "1.net.2.w"], W[e + "1.net.2.b"], residual=tok)
+        return ops.eltwise("scale", tok, s=2.0)   # "concat += _ximg" twice (:294-295), exact in fp16
+
+    def _local_tokens(self, local_first, W, b, h, w):
+        """local_image_embedding, unet_i2vgen.py:126-132,312-316 -> [b, 64, 1024] context tokens."""
+        x = ops.cp_to_pc(local_first.float().contiguous(), b, local_first.shape[1], h * w, c_pad=8).view(b, h, w, 8)
+        x = self._small_conv(x, W, "local_image_embedding.0.")
+        x = ops.adaptive_avgpool(x, 32, 32, silu_in=True)
+        x = self._small_conv(x, W, "local_image_embedding.3.", stride=2)
+        x = self._small_conv(x, W, "local_image_embedding.5.", stride=2, act_silu=True)
+        return x.view(b, -1, x.shape[-1])
+
+    @torch.no_grad()
+    def forward(self, x, t, y=None, image=None, local_image=None, masked=None, fps=None, video_mask=None,
+                focus_present_mask=None, prob_focus_present=0., mask_last_frame_num=0, **kwargs):
+        self._check_x(x, t)
+        if local_image is None or fps is None:
+            raise ValueError("UNetSD_I2VGen.forward needs local_image and fps")
+        W = self._packed or self._pack()
+        b, c, f, h, w = x.shape
+        if local_image.ndim == 5 and local_image.size(2) > 1:
+            local_image = local_image[:, :, :1]
+        elif local_image.ndim != 5:
+            local_image = local_image.unsqueeze(2)
+        cd = self.plan.concat_dim
+        concat = self._local_concat(local_image, W, b, f, h, w)                    # [(b f h w), cd]
+        emb = self._time_embedding(t, fps, W)
+        if y is None:
+            if self.zero_y is None:
+                raise ValueError("y is None and no zero_y was given")
+            y = self.zero_y.to(x.device).repeat(b, 1, 1)[:, :1, :]
+        y16 = self._to_f16_rows(y)
+        loc = self._local_tokens(local_image[:, :, 0], W, b, h, w)               # [b, 64, 1024]
+        parts = [y16, loc]
+        if image is not None:
+            img = self._to_f16_rows(image).view(-1, image.shape[-1])
+            ce = self._mlp(img, W, "context_embedding.")
+            parts.append(ce.view(b, self.num_tokens, self.context_dim))
+        ltot = sum(p.shape[1] for p in parts)
+        ctx = torch.empty(b, ltot, self.context_dim, device=x.device, dtype=torch.float16)
+        off = 0
+        for part in parts:
+            for bi in range(b):
+                ops.copy2d(part[bi], ctx[bi, off:off + part.shape[1]])
+            off += part.shape[1]
+        xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=c + cd).view(-1, c + cd)
+        ops.copy2d(concat, xin[:, c:])
+        out = self._trunk(xin.view(b * f, h, w, c + cd), emb, ctx, W, b, f)
+        return ops.pc_to_cp(out.view(b, f * h * w, self.out_dim), b, self.out_dim, f * h * w).view(b, self.out_dim, f, h, w)
