@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- denoise-steps/s (and decoded frames/s) of the VGen sampling hot path on B200.
+
+Workload (BASELINE.json configs[1]): i2vgen_xl, 16 frames, 1280x704 (latent [1,4,16,88,160]), DDIM
+with classifier-free guidance (2 UNet forwards + 1 fused DDIM update per step), synthetic image + text
+conditioning, random-init weights of the real architecture (UNetSD_I2VGen, 1.42 B parameters).
+A "step" is one denoising step.  N GPUs run N independent trajectories (weak scaling), the only
+collective is the one-time NCCL weight broadcast.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job steps/s with inputs
+resident in HBM; e2e = the same through the public DIFFUSION/MODEL API with HOST (pinned) buffers,
+H2D/D2H inside the timed region; roofline for the dominant kernel (tapgemm, tensor-bound); cpu_baseline =
+the oracle (CPU port of the reference) on a bounded sample.  `--impl reference` times that CPU oracle
+alone (the reference ships no CPU or Blackwell path of its own).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "i2vgen_xl_16f_1280x704_ddim_cfg"
+FRAMES, LAT_H, LAT_W = 16, 88, 160
+STEP_TFLOP = 176.19        # one CFG denoise step = 2 x 88.095 TFLOP
+UNET_KW = dict(in_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
+               head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], dropout=0.1, temporal_attention=True,
+               temporal_attn_times=1, use_checkpoint=True, use_fps_condition=False, use_sim_mask=False, concat_dim=4)
+VAE_KW = dict(ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                            ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0), embed_dim=4)
+DIFF_KW = dict(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+               mean_type="v", var_type="fixed_small", loss_type="mse", noise_strength=0.1)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs"), "tflops": d.get("bf16_tflops_sustained") or d.get("bf16_tflops"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _loop(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.25)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._loop, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_conditioning(seed, device):
+    """SURVEY.md section 8d synthetic inputs (CPU generator, then moved)."""
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn(1, 77, 1024, generator=g)
+    y_neg = torch.randn(1, 77, 1024, generator=g)
+    image = torch.randn(1, 1, 1024, generator=g)
+    local = (0.18215 * torch.randn(1, 4, 1, LAT_H, LAT_W, generator=g)).repeat(1, 1, FRAMES, 1, 1)
+    noise = torch.randn(1, 4, FRAMES, LAT_H, LAT_W, generator=g)
+    fps = torch.tensor([16], dtype=torch.long)
+    host = dict(y=y, y_neg=y_neg, image=image, local_image=local.contiguous(), noise=noise, fps=fps)
+    if device is None:
+        return host
+    return {k: v.to(device) for k, v in host.items()}
+
+
+def usable_cpus():
+    """Cores this process may actually run on: affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the host's cores, and oversubscribed OpenMP threads crawl)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt[0] != "max":
+            n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, min(n, 64))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline and --impl reference)
+_CPU_CACHE = {}
+
+
+def _cpu_oracle_setup(threads):
+    """Full-size UNetSD_I2VGen weights for the CPU oracle (values are irrelevant for timing: a 16M-value
+    random base is tiled with per-tensor scales, generated in ~1 s instead of 15 s of randn), the sample
+    inputs, and the sample's algorithmic FLOPs counted on meta tensors."""
+    if _CPU_CACHE:
+        return _CPU_CACHE
+    from torch.utils.flop_counter import FlopCounterMode
+
+    from oracle import vgen_oracle as vo
+    from vgen_b200 import arch
+    torch.set_num_threads(threads)
+    spec = arch.unet_spec(arch.unet_plan("i2vgen", **UNET_KW))
+    base = torch.randn(1 << 24, generator=torch.Generator().manual_seed(0))
+    sd = {}
+    off = 0
+    for name, shape in spec:
+        n = 1
+        for d in shape:
+            n *= d
+        fan = n // shape[0] if len(shape) > 1 else 1
+        reps = (n + base.numel() - 1) // base.numel()
+        if reps > 1:
+            flat = base.repeat(reps)[:n]
+        else:
+            st = (off * 7919) % (base.numel() - n + 1)
+            flat = base[st:st + n]
+        flat = flat * (fan ** -0.5 if len(shape) > 1 else 0.05)
+        if len(shape) == 1 and name.endswith("weight"):
+            flat = flat + 1.0
+        sd[name] = flat.reshape(shape).contiguous()
+        off += n
+    f, h, w = 4, 32, 32
+    gi = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, f, h, w, generator=gi)
+    kw = dict(y=torch.randn(1, 77, 1024, generator=gi), image=torch.randn(1, 1, 1024, generator=gi),
+              local_image=torch.randn(1, 4, f, h, w, generator=gi), fps=torch.tensor([16]))
+    msd = {n: torch.empty(s, device="meta") for n, s in spec}
+    mkw = {k: torch.empty(v.shape, device="meta", dtype=v.dtype) for k, v in kw.items()}
+    with torch.no_grad(), FlopCounterMode(display=False) as fc:
+        vo.unet_i2vgen_forward(msd, torch.empty(x.shape, device="meta"), torch.empty(1, device="meta", dtype=torch.long), **mkw)
+    _CPU_CACHE.update(sd=sd, x=x, kw=kw, fwd_flops=float(fc.get_total_flops()), shape=(f, h, w), vo=vo)
+    return _CPU_CACHE
+
+
+def cpu_oracle_sample(budget_s=15.0, threads=None, max_reps=4):
+    """Time the oracle (CPU restatement of the reference, fp32, all usable host cores) on a bounded
+    sample of the workload: CFG denoise steps (2 UNet forwards each) of the SAME 1.42B-parameter
+    architecture at a reduced latent, scaled to the metric's unit by algorithmic FLOPs."""
+    threads = threads or usable_cpus()
+    c = _cpu_oracle_setup(threads)
+    vo, sd, x, kw = c["vo"], c["sd"], c["x"], c["kw"]
+    t = torch.tensor([500])
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            vo.unet_i2vgen_forward(sd, x, t, **kw)
+            vo.unet_i2vgen_forward(sd, x, t, **kw)
+            n += 1
+            if time.perf_counter() - t0 > budget_s or n >= max_reps:
+                break
+        dt = time.perf_counter() - t0
+    tflops = 2 * n * c["fwd_flops"] / dt / 1e12
+    f, h, w = c["shape"]
+    return {"value": tflops / STEP_TFLOP, "unit": "denoise-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{n} CFG step(s) (2 forwards each) of UNetSD_I2VGen, full 1.42B-param architecture, fp32 oracle, latent "
+                      f"[1,4,{f},{h},{w}] ({c['fwd_flops'] / 1e12:.3f} TFLOP/forward) in {dt:.1f}s = {tflops:.3f} TFLOP/s; "
+                      f"scaled to the {STEP_TFLOP} TFLOP/step workload",
+            "cpu_tflops": tflops}
+
+
+def cpu_oracle_sample_subprocess(budget_s=15.0, timeout_s=240):
+    """Run the CPU baseline in a child process with a hard timeout so it can never stall the bench."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample", str(budget_s)], capture_output=True,
+                           text=True, timeout=timeout_s)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": "no output", "stderr": r.stderr[-400:]}
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout_s}s"}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    total_budget = 150.0
+    per = max(4.0, min(20.0, total_budget / max(1, args.steps + args.warmup)))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_oracle_sample(budget_s=per / 2, max_reps=1)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_oracle_sample(budget_s=per, max_reps=2)
+        vals.append(last["value"])
+    dt = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "denoise-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v if v > 0 else None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU oracle (port of the reference's PyTorch path; the reference has no CPU/Blackwell path of its own)"},
+            "cpu_baseline": dict(last, value=v), "e2e": {"value": v, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": dt}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=float, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--profile-pass", type=int, default=1, help="run one instrumented step for the roofline line")
+    args = ap.parse_args()
+
+    if args.cpu_sample is not None:
+        print(json.dumps(cpu_oracle_sample(budget_s=args.cpu_sample)), flush=True)
+        return 0
+    from vgen_b200 import parallel
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        return run_reference_arm(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: vgen_b200 has no CPU path"}))
+        return 1
+    rank, world, local_rank = parallel.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    import vgen_b200
+    from vgen_b200 import lib, ops
+    MODEL, DIFFUSION, AUTO_ENCODER = vgen_b200.register(force_local=True)
+    torch.manual_seed(1234)
+    model = MODEL.build(dict(type="UNetSD_I2VGen", **UNET_KW))
+    if rank != 0:  # only rank 0's weights matter: everyone else receives them over NCCL / NVLink
+        for p in model.parameters():
+            p.data.zero_()
+    # zero-initialised tensors (proj_out, ...) would make half the graph multiply by zero: randomise all
+    if rank == 0:
+        g = torch.Generator().manual_seed(4321)
+        for name, p in model.named_parameters():
+            if float(p.detach().abs().sum()) == 0.0:
+                p.data.normal_(0, 0.02, generator=g)
+    model = model.to(dev).eval()
+    bcast_bytes = parallel.broadcast_parameters(model, src=0)
+    diffusion = DIFFUSION.build(dict(type="DiffusionDDIM", **DIFF_KW))
+    c = synth_conditioning(8888 + rank, dev)
+    kw = [dict(y=c["y"], image=c["image"], local_image=c["local_image"], fps=c["fps"]),
+          dict(y=c["y_neg"], image=torch.zeros_like(c["image"]), local_image=c["local_image"], fps=c["fps"])]
+    ddim_T = 50
+    steps_all = diffusion.ddim_steps(ddim_T)
+
+    def one_step(xt, i):
+        step = int(steps_all[i % ddim_T])
+        t = torch.full((1,), step, dtype=torch.long, device=dev)
+        return diffusion._ddim_step(xt, step, t, model, kw, 9.0, ddim_T, 0.0)[0]
+
+    xt = c["noise"].clone()
+    for i in range(args.warmup):
+        xt = one_step(xt, i)
+    torch.cuda.synchronize()
+    parallel.barrier()
+
+    # ---- timed: K steps, inputs resident in HBM, CUDA events on the launching stream
+    l0 = lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(args.steps):
+            xt = one_step(xt, args.warmup + i)
+        ev1.record()
+        torch.cuda.synchronize()
+    launches = lib.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    parallel.barrier()
+    ms_max = parallel.max_over_ranks(ms, dev)
+    finite = bool(torch.isfinite(xt).all())
+
+    # ---- e2e: same step through the public API from HOST (pinned) buffers, H2D + D2H inside the timed region
+    host = synth_conditioning(8888 + rank, None)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    xt_host = pinned["noise"].clone().pin_memory()
+    out_host = torch.empty_like(xt_host).pin_memory()
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in ("y", "y_neg", "image", "local_image", "fps")) + xt_host.numel() * 4
+    d2h = out_host.numel() * 4
+
+    def e2e_step(i):
+        d = {k: pinned[k].to(dev, non_blocking=True) for k in ("y", "y_neg", "image", "local_image", "fps")}
+        x = xt_host.to(dev, non_blocking=True)
+        kws = [dict(y=d["y"], image=d["image"], local_image=d["local_image"], fps=d["fps"]),
+               dict(y=d["y_neg"], image=torch.zeros_like(d["image"]), local_image=d["local_image"], fps=d["fps"])]
+        step = int(steps_all[i % ddim_T])
+        t = torch.full((1,), step, dtype=torch.long, device=dev)
+        x, _ = diffusion.ddim_sample(x, t, model, kws, guide_scale=9.0, ddim_timesteps=ddim_T, eta=0.0)
+        out_host.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        xt_host.copy_(out_host)
+
+    e2e_step(0)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_e2e = max(2, min(args.steps, 4))
+    for i in range(n_e2e):
+        e2e_step(1 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    # ---- decode: AutoencoderKL.decode, 8 chunks x 2 frames (decoder_bs=2) of 1280x704
+    decode = None
+    if not args.no_decode:
+        vae = AUTO_ENCODER.build(dict(type="AutoencoderKL", **VAE_KW))
+        gv = torch.Generator().manual_seed(99)
+        for p in vae.parameters():
+            if p.dim() > 1:
+                p.data.normal_(0, (p[0].numel()) ** -0.5, generator=gv)
+        vae = vae.to(dev).eval()
+        z = (xt / 0.18215)[0].permute(1, 0, 2, 3).contiguous()            # [16, 4, 88, 160]
+        z = torch.nan_to_num(z).clamp(-10, 10)
+        vae.decode(z[:2])
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for i in range(0, FRAMES, 2):
+            img = vae.decode(z[i:i + 2])
+        d1.record()
+        torch.cuda.synchronize()
+        dms = parallel.max_over_ranks(d0.elapsed_time(d1), dev)
+        decode = {"frames_per_s": world * FRAMES / (dms / 1e3), "ms_per_16_frames": dms, "dtype": "f16 activations / f32 accumulate",
+                  "finite": bool(torch.isfinite(img).all())}
+        del vae, img
+
+    # ---- instrumented pass: per-kernel-family device time (CUDA events) for the roofline line
+    roofline = None
+    families = None
+    if args.profile_pass and rank == 0:
+        ops.PROF = ops.KernelProfile()
+        xt2 = one_step(xt, 0)
+        summ = ops.PROF.summary()
+        ops.PROF = None
+        del xt2
+        families = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / 1e9 / max(v["ms"], 1e-9), 1) if v["flops"] else None,
+                        "gbs": round(v["bytes"] / 1e6 / max(v["ms"], 1e-9), 1)} for k, v in summ.items()}
+        tg = summ.get("tapgemm")
+        pk = measured_peaks()
+        if tg:
+            ach = tg["flops"] / (tg["ms"] / 1e3) / 1e12
+            roofline = {"kernel": "tapgemm_sm100_kernel (conv3x3 / temporal conv / linear, tcgen05)", "bound": "tensor",
+                        "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                        "launches_per_step": tg["launches"], "avg_launch_ms": tg["ms"] / tg["launches"],
+                        "algorithmic_tflop_per_step": tg["flops"] / 1e12, "peak_source": pk["source"]}
+
+    value = world * args.steps / (ms_max / 1e3)
+    line = {"metric": "denoise_steps_per_s", "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "latent": [1, 4, FRAMES, LAT_H, LAT_W], "forwards_per_step": 2, "guide_scale": 9.0,
+                       "l2": "inputs larger than L2 (2.8 GB of weights + >100 MB activations stream per forward)",
+                       "parallelism": f"{world} independent trajectories (no data-path collective)",
+                       "weight_broadcast_bytes": bcast_bytes},
+            "e2e": {"value": world * n_e2e / (e2e_ms / 1e3), "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clk.summary(), "finite": finite,
+            "tflops_effective": value * STEP_TFLOP / world, "decode": decode, "roofline": roofline, "kernel_families": families}
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_oracle_sample_subprocess(budget_s=15.0)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    parallel.barrier()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,193 @@
+"""Host-side logic that needs no GPU: parameter specs, strict state_dict compatibility, registry
+contract, DDIM host math (bit-exact), C-ABI surface, multi-process sharding/broadcast over gloo."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import vgen_b200
+from oracle import synth, vgen_oracle as vo
+from oracle.cases import CASES, FULL_CTORS
+from vgen_b200 import arch, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gold_spec(golden_dir, name):
+    return [(k, tuple(s)) for k, s in json.load(open(os.path.join(golden_dir, f"{name}.spec.json")))]
+
+
+@pytest.mark.parametrize("name", list(CASES) + list(FULL_CTORS))
+def test_param_spec_equals_reference(golden_dir, name):
+    kind, ctor = (CASES[name]["kind"], CASES[name]["ctor"]) if name in CASES else FULL_CTORS[name]
+    if kind == "vae":
+        mine = arch.vae_spec(arch.vae_plan(ctor["ddconfig"], ctor["embed_dim"]))
+    else:
+        mine = arch.unet_spec(arch.unet_plan(kind, **ctor))
+    assert mine == _gold_spec(golden_dir, name)       # names, shapes AND registration order
+
+
+def test_full_size_tensor_counts(golden_dir):
+    assert len(_gold_spec(golden_dir, "full_t2v")) == 1480
+    assert len(_gold_spec(golden_dir, "full_i2vgen")) == 1509
+    assert len(_gold_spec(golden_dir, "full_vae")) == 248
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_strict_state_dict_roundtrip(golden_dir, name):
+    case = CASES[name]
+    cls = {"t2v": vgen_b200.UNetSD_T2VBase, "i2vgen": vgen_b200.UNetSD_I2VGen, "vae": vgen_b200.AutoencoderKL}[case["kind"]]
+    m = cls(**case["ctor"])
+    spec = _gold_spec(golden_dir, name)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == spec
+    sd = synth.state_dict(spec, seed=case["seed"])
+    m.load_state_dict(sd, strict=True)
+    assert torch.equal(m.state_dict()[spec[5][0]], sd[spec[5][0]])
+    assert any(p.requires_grad for p in m.parameters())          # DistributedDataParallel needs one
+    bad = dict(sd)
+    bad.pop(spec[0][0])
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+
+
+def test_registry_contract():
+    M, D, A = vgen_b200.register(force_local=True)
+    case = CASES["t2v_tiny"]
+    # YAML dicts carry extra keys (upper_len, default_fps, misc_dropout ...): constructors must swallow them
+    m = M.build(dict(type="UNetSD_T2VBase", **case["ctor"], upper_len=128, default_fps=8, misc_dropout=0.4))
+    assert type(m).__name__ == "UNetSD_T2VBase" and m.device.type == "cpu"
+    with pytest.raises(KeyError):
+        M.build(dict(type="NoSuchModel"))
+    with pytest.raises(Exception, match="Failed to init class"):
+        M.build(dict(type="UNetSD_T2VBase", **dict(case["ctor"], head_dim=32)))
+    d = D.build(dict(type="DiffusionDDIM", schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+                     mean_type="v", var_type="fixed_small", loss_type="mse", noise_strength=0.1))
+    assert d.num_timesteps == 1000
+    a = A.build(dict(type="AutoencoderKL", **CASES["vae_tiny"]["ctor"]))
+    assert hasattr(a, "decode") and hasattr(a, "encode_firsr_stage")
+
+
+def test_registers_into_reference_registry_when_available():
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference not mounted")
+    ref = refload.load()
+    M, D, A = vgen_b200.register()
+    assert M is ref.registry.MODEL and D is ref.registry.DIFFUSION and A is ref.registry.AUTO_ENCODER
+    assert M.get("UNetSD_I2VGen") is vgen_b200.UNetSD_I2VGen and D.get("DiffusionDDIM") is vgen_b200.DiffusionDDIM
+    # restore the reference classes for the other tests in this process
+    M.register_class()(ref.UNetSD_T2VBase), M.register_class()(ref.UNetSD_I2VGen)
+    D.register_class()(ref.DiffusionDDIM), A.register_class()(ref.AutoencoderKL)
+
+
+def test_no_cpu_fallback():
+    case = CASES["t2v_tiny"]
+    m = vgen_b200.UNetSD_T2VBase(**case["ctor"])
+    with pytest.raises(Exception, match="CUDA"):
+        m(torch.zeros(1, 4, 2, 8, 8), torch.zeros(1, dtype=torch.long), y=torch.zeros(1, 5, 1024))
+    v = vgen_b200.AutoencoderKL(**CASES["vae_tiny"]["ctor"])
+    with pytest.raises(Exception, match="CUDA"):
+        v.decode(torch.zeros(1, 4, 8, 8))
+
+
+def test_product_never_imports_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "vgen_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "vgen_b200", fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), fn
+
+
+# ------------------------------------------------------------------------------------ DDIM host math
+def test_ddim_tables_and_steps_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "schedules.npz"))
+    d = vgen_b200.DiffusionDDIM(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+                                mean_type="v", var_type="fixed_small")
+    assert np.array_equal(d.betas.numpy(), g["cosine_zsnr.betas"])
+    assert np.array_equal(d.alphas_cumprod.numpy(), g["cosine_zsnr.alphas_cumprod"])
+    d2 = vgen_b200.DiffusionDDIM(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085, last_beta=0.012, zero_terminal_snr=True),
+                                 mean_type="v", var_type="fixed_small")
+    assert np.array_equal(d2.alphas_cumprod.numpy(), g["linear_sd_zsnr.alphas_cumprod"])
+    for S in (50, 4, 20):
+        assert np.array_equal(d.ddim_steps(S).numpy(), g[f"steps_{S}"])
+
+
+def test_ddim_step_coefficients_match_reference_formulas():
+    d = vgen_b200.DiffusionDDIM(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+                                mean_type="v", var_type="fixed_small")
+    tab = vo.ddim_tables(vo.make_betas("cosine", 1000, True, cosine_s=0.008))
+    for S in (50, 4):
+        stride = 1000 // S
+        for step in d.ddim_steps(S).tolist():
+            c = d.step_coefficients(step, S, 0.0)
+            f32 = torch.float32
+            a_prev = tab["alphas_cumprod"][max(step - stride, 0)].to(f32)
+            want = [tab["sqrt_alphas_cumprod"][step].to(f32), tab["sqrt_one_minus_alphas_cumprod"][step].to(f32),
+                    tab["sqrt_recip_alphas_cumprod"][step].to(f32), tab["sqrt_recipm1_alphas_cumprod"][step].to(f32),
+                    torch.sqrt(a_prev), torch.sqrt(1 - a_prev), torch.tensor(0.0)]
+            assert c == [float(w) for w in want]
+    # last step uses alphas_cumprod[0], not 1 (diffusion_ddim.py:233)
+    assert d.step_coefficients(1, 50, 0.0)[4] == float(torch.sqrt(tab["alphas_cumprod"][0].to(torch.float32)))
+    with pytest.raises(NotImplementedError):
+        d.ddim_sample(torch.zeros(1, 4, 1, 2, 2), torch.tensor([1]), lambda *a, **k: None, {}, clamp=1.0)
+
+
+# ------------------------------------------------------------------------------------ C ABI surface
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "vgen_b200.h")).read()
+    declared = set(re.findall(r"\b(vgen_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(lib.declared_symbols()), declared ^ set(lib.declared_symbols())
+    dll = ctypes.CDLL(str(lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(dll, name), name
+    l = lib.load()
+    assert l.vgen_abi_version() == 1 and l.vgen_launch_count() == 0
+    assert l.vgen_set_tapgemm_impl(7) != 0 and b"impl" in l.vgen_last_error()
+    assert l.vgen_set_tapgemm_impl(0) == 0
+    assert l.vgen_group_norm_workspace_bytes(2) > 0
+    assert ctypes.sizeof(lib.Epilogue) == 64       # struct vgen_epilogue layout (x86-64 SysV)
+
+
+# ------------------------------------------------------------------------------------ multi-process (gloo)
+_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from vgen_b200 import parallel
+import vgen_b200
+from oracle.cases import CASES
+rank, world, _ = parallel.init_from_env("gloo")
+torch.manual_seed(100 + rank)                       # every rank starts from DIFFERENT weights
+m = vgen_b200.AutoencoderKL(**CASES["vae_tiny"]["ctor"])
+for p in m.parameters():
+    p.data.normal_()
+nbytes = parallel.broadcast_parameters(m, src=0, bucket_bytes=1 << 20)
+chk = torch.cat([p.data.reshape(-1) for p in m.parameters()]).double().sum()
+allc = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(allc, chk)
+assert all(float(c) == float(allc[0]) for c in allc), allc
+assert nbytes == sum(p.numel() * 4 for p in m.parameters())
+prompts = [f"p{i}" for i in range(8)]
+mine = parallel.shard_items(prompts, rank, world)
+got = [None] * world
+dist.all_gather_object(got, mine)
+assert sorted(sum(got, [])) == sorted(prompts) and all(len(g) == 4 for g in got)
+assert parallel.shard_items(prompts, rank, world, "replicate") == prompts
+assert parallel.max_over_ranks(float(rank)) == float(world - 1)
+parallel.barrier()
+print("RANK_OK", rank)
+'''
+
+
+def test_gloo_world2_broadcast_and_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout

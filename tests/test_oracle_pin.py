@@ -1,0 +1,46 @@
+"""Direct pin of the oracle against the real reference classes (only where /root/reference is mounted)."""
+import pytest
+import torch
+
+from oracle import refload, synth, vgen_oracle as vo
+from oracle.cases import CASES, make_inputs
+
+pytestmark = pytest.mark.skipif(not refload.available(), reason="reference not mounted (GPU box)")
+
+
+def _maxrel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def test_unet_t2v_against_reference_class():
+    torch.set_grad_enabled(False)
+    ref = refload.load()
+    case = CASES["t2v_tiny_b2"]
+    m = ref.UNetSD_T2VBase(**case["ctor"]).eval()
+    sd = synth.state_dict(synth.spec_of(m), seed=77)          # a seed the golden files do not use
+    m.load_state_dict(sd, strict=True)
+    inp = make_inputs(case)
+    assert _maxrel(vo.unet_t2v_forward(sd, inp["x"], inp["t"], inp["y"]), m(inp["x"], inp["t"], y=inp["y"])) < 2e-5
+
+
+def test_default_init_is_degenerate_and_synth_is_not():
+    """SURVEY.md section 8c hygiene: with the reference's default init the output is a per-channel constant."""
+    torch.set_grad_enabled(False)
+    ref = refload.load()
+    case = CASES["t2v_tiny"]
+    torch.manual_seed(0)
+    m = ref.UNetSD_T2VBase(**case["ctor"]).eval()
+    inp = make_inputs(case)
+    out = m(inp["x"], inp["t"], y=inp["y"])
+    assert float(out.std(dim=(2, 3, 4)).max()) < 1e-6
+    m.load_state_dict(synth.state_dict(synth.spec_of(m), seed=case["seed"]), strict=True)
+    assert float(m(inp["x"], inp["t"], y=inp["y"]).std()) > 0.1
+
+
+def test_ddim_tables_against_reference_class():
+    ref = refload.load()
+    d = ref.DiffusionDDIM(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+                          mean_type="v", var_type="fixed_small")
+    tab = vo.ddim_tables(vo.make_betas("cosine", 1000, True, cosine_s=0.008))
+    for k, v in tab.items():
+        assert torch.equal(v, getattr(d, k)), k

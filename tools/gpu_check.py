@@ -349,7 +349,8 @@ def group_elementwise():
         y, u = rnd(1, 4, 4, 8, 12).half(), rnd(1, 4, 4, 8, 12).half()
         coef = [0.6, 0.8, 1.0 / 0.6, (1 / 0.36 - 1) ** 0.5, 0.7, (1 - 0.49) ** 0.5, 0.0]
         out = u + 9.0 * (y - u)           # fp16 tensor arithmetic, like the reference under autocast
-        ct = [torch.tensor(v, device="cuda", dtype=torch.float32) for v in coef]  # _i() yields fp32 tensors
+        # _i() yields fp32 tensors of shape [b,1,1,1,1] (dimensioned, so they take part in type promotion)
+        ct = [torch.tensor(v, device="cuda", dtype=torch.float32).view(1, 1, 1, 1, 1) for v in coef]
         x0 = ct[0] * xt - ct[1] * out
         eps = (ct[2] * xt - x0) / ct[3]
         ref = ct[4] * x0 + ct[5] * eps

@@ -1,5 +1,6 @@
 // GroupNorm(32) (+SiLU) and LayerNorm on channels-last fp16 activations: HBM-bound kernels with
-// 16-byte vectorised, fully coalesced accesses and fp32 statistics.
+// 16-byte vectorised, fully coalesced accesses, several independent loads in flight per thread and
+// fp32 statistics.
 //
 // Reference ops replaced:
 //   nn.GroupNorm(32, C) + nn.SiLU in ResBlock in_layers/out_layers   tools/modules/unet/util.py:845-876
@@ -10,18 +11,21 @@
 // Under the reference's autocast these run in fp32 and the result is rounded to fp16 once by the
 // consuming conv/linear; the kernels below do the same (fp32 maths, one fp16 rounding at the store).
 //
-// GroupNorm is two launches:
-//   gn_stats : grid (splits, N): per-channel fp32 sum / sum-of-squares in registers (each thread owns
-//              fixed channel vectors, so no atomics), folded to per-group (mean, M2) partials.
-//   gn_apply : combines the partials with Chan's formula (robust to mean >> std), then
-//              y = silu?(x * scale_c + shift_c) streamed with 16-byte loads/stores.
+// GroupNorm is three launches:
+//   gn_stats    grid (splits, N): each thread owns fixed channel vectors (no atomics) and accumulates
+//               per-channel fp32 sum / sum-of-squares over its pixels, 4 loads in flight; folded to
+//               per-group (mean, M2) partials.  The split count scales with the tensor so that even the
+//               N = 1 "all frames jointly" norms fill the 148 SMs.
+//   gn_finalize grid (N): one warp per group merges the partials with Chan's formula (robust to
+//               mean >> std) -> (mean, rstd).
+//   gn_apply    same thread->channel ownership, scale/shift in registers: y = silu?(x*scale + shift).
 #include "common.h"
 #include "ptx.cuh"
 
 namespace vg {
 
 static constexpr int kGroups = 32;
-static constexpr int kMaxSplits = 64;
+static constexpr int kMaxSplits = 1024;
 
 struct GnGeom {
   int C, C8, cpg;      // channels, C/8, channels per group
@@ -32,6 +36,18 @@ struct GnGeom {
   int splits;
   long chunk;          // positions per split
 };
+
+__device__ __forceinline__ void acc8(const uint4& u, float (&s)[8], float (&q)[8]) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h2[i]);
+    s[2 * i] += f.x;
+    q[2 * i] = fmaf(f.x, f.x, q[2 * i]);
+    s[2 * i + 1] += f.y;
+    q[2 * i + 1] = fmaf(f.y, f.y, q[2 * i + 1]);
+  }
+}
 
 template <int VPT>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, float2* __restrict__ partial, GnGeom g) {
@@ -50,22 +66,26 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
 
   if (r < g.rows) {
     const __half* base = x + ((long)n * g.P) * g.C;
-    for (long p = p0 + r; p < p1; p += g.rows) {
+    const long step = g.rows;
 #pragma unroll
-      for (int j = 0; j < VPT; ++j) {
-        const int v = cv + j * g.cols;
-        if (v < g.C8) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * g.C + v * 8));
-          const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h2[i]);
-            s[j][2 * i] += f.x;
-            q[j][2 * i] += f.x * f.x;
-            s[j][2 * i + 1] += f.y;
-            q[j][2 * i + 1] += f.y * f.y;
-          }
-        }
+    for (int j = 0; j < VPT; ++j) {
+      const int v = cv + j * g.cols;
+      if (v >= g.C8) continue;
+      const __half* col = base + v * 8;
+      long p = p0 + r;
+      for (; p + 3 * step < p1; p += 4 * step) {  // 4 independent 16-byte loads in flight
+        const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(col + p * g.C));
+        const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(col + (p + step) * g.C));
+        const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(col + (p + 2 * step) * g.C));
+        const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(col + (p + 3 * step) * g.C));
+        acc8(u0, s[j], q[j]);
+        acc8(u1, s[j], q[j]);
+        acc8(u2, s[j], q[j]);
+        acc8(u3, s[j], q[j]);
+      }
+      for (; p < p1; p += step) {
+        const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(col + p * g.C));
+        acc8(u0, s[j], q[j]);
       }
     }
     float* ss = sm + (long)r * g.C;
@@ -101,73 +121,116 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
   }
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
-
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
-                                                       const float2* __restrict__ partial,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       GnGeom g, float eps, int silu, long apply_chunk) {
-  extern __shared__ float sm[];  // scale[C], shift[C], mean[32], rstd[32]
-  float* scale = sm;
-  float* shift = sm + g.C;
-  float* gmean = sm + 2 * g.C;
-  float* grstd = gmean + kGroups;
-  const int n = blockIdx.y;
-  if (threadIdx.x < kGroups) {
-    // Chan et al. parallel combination of (count, mean, M2)
-    float cnt = 0.f, mean = 0.f, m2 = 0.f;
-    for (int sp = 0; sp < g.splits; ++sp) {
+// one warp per group: lanes stride over the splits, then a shuffle tree of Chan merges
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats,
+                                                           GnGeom g, float eps) {
+  const int n = blockIdx.x;
+  const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  const float2* pbase = partial + (long)n * g.splits * kGroups + grp;
+  for (int sp0 = lane; sp0 < g.splits; sp0 += 32 * 8) {
+    float2 pm[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {  // 8 independent loads in flight, then the (serial) Chan merges
+      const int sp = sp0 + u * 32;
+      pm[u] = sp < g.splits ? __ldg(pbase + (long)sp * kGroups) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int sp = sp0 + u * 32;
+      if (sp >= g.splits) continue;
       const long q0 = (long)sp * g.chunk;
       long q1 = q0 + g.chunk;
       if (q1 > g.P) q1 = g.P;
       if (q1 <= q0) continue;
       const float cb = (float)((q1 - q0) * g.cpg);
-      const float2 pm = partial[((long)n * g.splits + sp) * kGroups + threadIdx.x];
       const float tot = cnt + cb;
-      const float delta = pm.x - mean;
+      const float delta = pm[u].x - mean;
       mean += delta * (cb / tot);
-      m2 += pm.y + delta * delta * (cnt * cb / tot);
+      m2 += pm[u].y + delta * delta * (cnt * cb / tot);
       cnt = tot;
     }
-    gmean[threadIdx.x] = mean;
-    grstd[threadIdx.x] = rsqrtf(m2 / cnt + eps);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
-    const int grp = c / g.cpg;
-    const float sc = grstd[grp] * gamma[c];
-    scale[c] = sc;
-    shift[c] = beta[c] - gmean[grp] * sc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float cb = __shfl_xor_sync(0xffffffffu, cnt, o);
+    const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+    const float qb = __shfl_xor_sync(0xffffffffu, m2, o);
+    const float tot = cnt + cb;
+    if (tot > 0.f) {
+      const float delta = mb - mean;
+      mean += delta * (cb / tot);
+      m2 += qb + delta * delta * (cnt * cb / tot);
+      cnt = tot;
+    }
   }
-  __syncthreads();
+  if (lane == 0) stats[(long)n * kGroups + grp] = make_float2(mean, rsqrtf(m2 / cnt + eps));
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ uint4 norm8(const uint4& u, const float (&sc)[8], const float (&sh)[8], int silu) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __half22float2(h2[k]);
+    f[2 * k] = fmaf(t.x, sc[2 * k], sh[2 * k]);
+    f[2 * k + 1] = fmaf(t.y, sc[2 * k + 1], sh[2 * k + 1]);
+  }
+  if (silu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+  }
+  uint4 o;
+  o.x = pack_half2(f[0], f[1]);
+  o.y = pack_half2(f[2], f[3]);
+  o.z = pack_half2(f[4], f[5]);
+  o.w = pack_half2(f[6], f[7]);
+  return o;
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                       const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, GnGeom g, int silu, long apply_chunk) {
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int r = tid / g.cols, cv = tid - r * g.cols;
+  if (r >= g.rows) return;
   const long p0 = (long)blockIdx.x * apply_chunk;
   long p1 = p0 + apply_chunk;
   if (p1 > g.P) p1 = g.P;
-  const long nvec = (p1 - p0) * g.C8;
-  const __half* xb = x + ((long)n * g.P + p0) * g.C;
-  __half* yb = y + ((long)n * g.P + p0) * g.C;
-  for (long i = threadIdx.x; i < nvec; i += blockDim.x) {
-    const int v = (int)(i % g.C8);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
-    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-    float f[8];
+  const long step = g.rows;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 t = __half22float2(h2[k]);
-      f[2 * k] = t.x;
-      f[2 * k + 1] = t.y;
-    }
+  for (int j = 0; j < VPT; ++j) {
+    const int v = cv + j * g.cols;
+    if (v >= g.C8) continue;
+    float sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float t = f[k] * scale[v * 8 + k] + shift[v * 8 + k];
-      f[k] = silu ? silu_f(t) : t;
+      const int c = v * 8 + k;
+      const float2 st = __ldg(stats + (long)n * kGroups + c / g.cpg);
+      sc[k] = st.y * __ldg(gamma + c);
+      sh[k] = __ldg(beta + c) - st.x * sc[k];
     }
-    uint4 o;
-    o.x = pack_half2(f[0], f[1]);
-    o.y = pack_half2(f[2], f[3]);
-    o.z = pack_half2(f[4], f[5]);
-    o.w = pack_half2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(yb + i * 8) = o;
+    const __half* xc = x + ((long)n * g.P) * g.C + v * 8;
+    __half* yc = y + ((long)n * g.P) * g.C + v * 8;
+    long p = p0 + r;
+    for (; p + 3 * step < p1; p += 4 * step) {
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(xc + p * g.C));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(xc + (p + step) * g.C));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(xc + (p + 2 * step) * g.C));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(xc + (p + 3 * step) * g.C));
+      *reinterpret_cast<uint4*>(yc + p * g.C) = norm8(u0, sc, sh, silu);
+      *reinterpret_cast<uint4*>(yc + (p + step) * g.C) = norm8(u1, sc, sh, silu);
+      *reinterpret_cast<uint4*>(yc + (p + 2 * step) * g.C) = norm8(u2, sc, sh, silu);
+      *reinterpret_cast<uint4*>(yc + (p + 3 * step) * g.C) = norm8(u3, sc, sh, silu);
+    }
+    for (; p < p1; p += step) {
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(xc + p * g.C));
+      *reinterpret_cast<uint4*>(yc + p * g.C) = norm8(u0, sc, sh, silu);
+    }
   }
 }
 
@@ -182,10 +245,10 @@ static int gn_geometry(long N, long P, int C, GnGeom* g) {
   g->rows = 256 / g->cols;
   if (g->rows < 1) g->rows = 1;
   g->P = P;
-  long want = (4L * sm_count()) / (N > 0 ? N : 1);
+  long want = (8L * sm_count()) / (N > 0 ? N : 1);  // ~8 blocks per SM over the whole launch
   if (want < 1) want = 1;
   if (want > kMaxSplits) want = kMaxSplits;
-  long min_chunk = 4L * g->rows;  // at least a few iterations per block
+  long min_chunk = 8L * g->rows;  // at least two unrolled iterations per thread
   long chunk = (P + want - 1) / want;
   if (chunk < min_chunk) chunk = min_chunk;
   g->chunk = chunk;
@@ -194,63 +257,86 @@ static int gn_geometry(long N, long P, int C, GnGeom* g) {
 }
 
 // ------------------------------------------------------------------------------- LayerNorm
-// one warp per row; the row lives in registers (C <= 2560), two-pass mean / variance like ATen.
+// One warp per row, the row lives in registers (C <= 2560), two-pass mean / variance like ATen.  Warps
+// walk rows with a grid stride and prefetch the next row's raw vectors before reducing the current one,
+// so every warp always has loads in flight.
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long rows, int C, long ldx, long ldy, float eps) {
-  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int C8 = C >> 3;
-  const __half* xr = x + row * ldx;
-  float f[MAXV][8];
-  float s = 0.f;
+  const long warps_total = (long)gridDim.x * (blockDim.x >> 5);
+  long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  uint4 nxt[MAXV];
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     const int v = lane + j * 32;
-    if (v < C8) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    if (v < C8) nxt[j] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8));
+  }
+  for (; row < rows; row += warps_total) {
+    float f[MAXV][8];
+    float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 t = __half22float2(h2[k]);
-        f[j][2 * k] = t.x;
-        f[j][2 * k + 1] = t.y;
-        s += t.x + t.y;
+    for (int j = 0; j < MAXV; ++j) {
+      const int v = lane + j * 32;
+      if (v < C8) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&nxt[j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t = __half22float2(h2[k]);
+          f[j][2 * k] = t.x;
+          f[j][2 * k + 1] = t.y;
+          s += t.x + t.y;
+        }
       }
     }
-  }
-  s = warp_sum(s);
-  const float mean = s / (float)C;
-  float q = 0.f;
+    const long nrow = row + warps_total;
+    if (nrow < rows) {
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < C8) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float d = f[j][k] - mean;
-        q += d * d;
+      for (int j = 0; j < MAXV; ++j) {
+        const int v = lane + j * 32;
+        if (v < C8) nxt[j] = __ldg(reinterpret_cast<const uint4*>(x + nrow * ldx + v * 8));
       }
     }
-  }
-  q = warp_sum(q);
-  const float rstd = rsqrtf(q / (float)C + eps);
-  __half* yr = y + row * ldy;
+    s = warp_sum(s);
+    const float mean = s / (float)C;
+    float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < C8) {
-      float o[8];
+    for (int j = 0; j < MAXV; ++j) {
+      const int v = lane + j * 32;
+      if (v < C8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (f[j][k] - mean) * rstd * __ldg(gamma + v * 8 + k) + __ldg(beta + v * 8 + k);
-      uint4 u;
-      u.x = pack_half2(o[0], o[1]);
-      u.y = pack_half2(o[2], o[3]);
-      u.z = pack_half2(o[4], o[5]);
-      u.w = pack_half2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(yr + v * 8) = u;
+        for (int k = 0; k < 8; ++k) {
+          const float d = f[j][k] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    __half* yr = y + row * ldy;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int v = lane + j * 32;
+      if (v < C8) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf((f[j][k] - mean) * rstd, gg[k], bb[k]);
+        uint4 u;
+        u.x = pack_half2(o[0], o[1]);
+        u.y = pack_half2(o[2], o[3]);
+        u.z = pack_half2(o[4], o[5]);
+        u.w = pack_half2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(yr + v * 8) = u;
+      }
     }
   }
 }
@@ -280,7 +366,11 @@ using namespace vg;
 
 extern "C" {
 
-int64_t vgen_group_norm_workspace_bytes(int64_t n) { return (n < 1 ? 1 : n) * (int64_t)kMaxSplits * kGroups * sizeof(float2); }
+// workspace: [n][kMaxSplits][32] partials + [n][32] final (mean, rstd)
+int64_t vgen_group_norm_workspace_bytes(int64_t n) {
+  const int64_t nn = n < 1 ? 1 : n;
+  return nn * (int64_t)(kMaxSplits + 1) * kGroups * (int64_t)sizeof(float2);
+}
 
 int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, const float* gamma, const float* beta,
                     float eps, int silu, void* workspace, void* stream) {
@@ -294,6 +384,7 @@ int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, con
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float2* part = reinterpret_cast<float2*>(workspace);
+  float2* stats = part + (long)n * kMaxSplits * kGroups;
   const size_t smem_stats = (size_t)2 * g.rows * g.C * sizeof(float);
   VG_REQUIRE(smem_stats <= 48 * 1024, "vgen_group_norm: stats smem too large");
   dim3 grid_s(g.splits, (unsigned)n);
@@ -303,16 +394,20 @@ int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, con
   else
     gn_stats_kernel<2><<<grid_s, threads, smem_stats, st>>>(reinterpret_cast<const __half*>(x), part, g);
   VG_LAUNCH_CHECK("gn_stats_kernel");
-  // apply: ~4 waves of blocks
-  long blocks = (4L * sm_count()) / n;
+  gn_finalize_kernel<<<(unsigned)n, 1024, 0, st>>>(part, stats, g, eps);
+  VG_LAUNCH_CHECK("gn_finalize_kernel");
+  long blocks = (8L * sm_count()) / n;
   if (blocks < 1) blocks = 1;
   long apply_chunk = (p + blocks - 1) / blocks;
-  if (apply_chunk < 8) apply_chunk = 8;
+  if (apply_chunk < 8L * g.rows) apply_chunk = 8L * g.rows;
   blocks = (p + apply_chunk - 1) / apply_chunk;
   dim3 grid_a((unsigned)blocks, (unsigned)n);
-  const size_t smem_apply = (size_t)(2 * g.C + 2 * kGroups) * sizeof(float);
-  gn_apply_kernel<<<grid_a, 256, smem_apply, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), part,
-                                                   gamma, beta, g, eps, silu, apply_chunk);
+  if (g.vpt == 1)
+    gn_apply_kernel<1><<<grid_a, threads, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), stats, gamma,
+                                                   beta, g, silu, apply_chunk);
+  else
+    gn_apply_kernel<2><<<grid_a, threads, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), stats, gamma,
+                                                   beta, g, silu, apply_chunk);
   VG_LAUNCH_CHECK("gn_apply_kernel");
   return 0;
 }
@@ -326,19 +421,22 @@ int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx
   const __half* xp = reinterpret_cast<const __half*>(x);
   __half* yp = reinterpret_cast<__half*>(y);
   const bool vec = (c % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && c <= 2560;
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && c <= 2560 &&
+                   ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
   if (vec) {
     const int wpb = 8;
-    const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
+    long blocks = (rows + wpb - 1) / wpb;
+    const long cap = 16L * sm_count();  // grid-stride: ~16 resident blocks' worth per SM
+    if (blocks > cap) blocks = cap;
     const int c8 = (int)c / 8;
     if (c8 <= 32)
-      layernorm_kernel<1><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      layernorm_kernel<1><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     else if (c8 <= 64)
-      layernorm_kernel<2><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      layernorm_kernel<2><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     else if (c8 <= 160)
-      layernorm_kernel<5><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      layernorm_kernel<5><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     else
-      layernorm_kernel<10><<<blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      layernorm_kernel<10><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     VG_LAUNCH_CHECK("layernorm_kernel");
   } else {
     const unsigned blocks = (unsigned)((rows + 127) / 128);

@@ -14,6 +14,42 @@ from . import lib as _l
 from .lib import Epilogue
 
 
+class KernelProfile:
+    """Optional per-kernel-family device timing (CUDA events on the launching stream) + algorithmic
+    work counters.  Used by bench.py for the roofline line; off by default (PROF is None)."""
+
+    def __init__(self):
+        self.records = []  # (family, flops, bytes, start_event, stop_event)
+
+    def run(self, family, flops, nbytes, fn):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn()
+        e.record()
+        self.records.append((family, float(flops), float(nbytes), s, e))
+        return rc
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, fl, nb, s, e in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += nb
+        return out
+
+
+PROF = None  # set to a KernelProfile() to instrument calls
+
+
+def _run(family, flops, nbytes, fn):
+    if PROF is None:
+        return fn()
+    return PROF.run(family, flops, nbytes, fn)
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -79,7 +115,8 @@ def linear(a, w, bias=None, residual=None, alpha=1.0, geglu=False, out=None, bn=
         out = torch.empty(*lead, n_out, device=a.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
     e, keep = _epilogue(n_out, bias, None, residual, alpha, geglu, bn)
-    rc = _l.load().vgen_linear(_p(a2), m, k, lda, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream())
+    rc = _run("tapgemm", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n_out),
+              lambda: _l.load().vgen_linear(_p(a2), m, k, lda, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()))
     _l.check(rc, "vgen_linear")
     return out
 
@@ -97,7 +134,9 @@ def conv2d_3x3(x, w, bias=None, group_bias=None, residual=None, out=None, bn=0, 
         out = torch.empty(nimg, h, wd, n, device=x.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
     e, keep = _epilogue(n, bias, group_bias, residual, 1.0, False, bn, group_div)
-    rc = _l.load().vgen_conv2d_3x3(_p(x), nimg, h, wd, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream())
+    rows = nimg * h * wd
+    rc = _run("tapgemm", 2.0 * rows * n * 9 * c, 2.0 * (rows * c + 9 * c * n + rows * n),
+              lambda: _l.load().vgen_conv2d_3x3(_p(x), nimg, h, wd, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()))
     _l.check(rc, "vgen_conv2d_3x3")
     return out
 
@@ -115,7 +154,8 @@ def tconv3(x, w, bias=None, residual=None, out=None, bn=0):
         out = torch.empty(f, hw, n, device=x.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
     e, keep = _epilogue(n, bias, None, residual, 1.0, False, bn)
-    rc = _l.load().vgen_tconv3(_p(x), f, hw, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream())
+    rc = _run("tapgemm", 2.0 * f * hw * n * 3 * c, 2.0 * (f * hw * c + 3 * c * n + f * hw * n),
+              lambda: _l.load().vgen_tconv3(_p(x), f, hw, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()))
     _l.check(rc, "vgen_tconv3")
     return out
 
@@ -170,8 +210,9 @@ def group_norm(x, gamma, beta, eps, silu, n=None, out=None):
     if out is None:
         out = torch.empty_like(x)
     ws = _gn_workspace(x.device, n)
-    rc = _l.load().vgen_group_norm(_p(x), _p(out), n, p, c, _p(gamma), _p(beta), float(eps), 1 if silu else 0,
-                                   _p(ws), _stream())
+    rc = _run("group_norm", 0.0, 4.0 * x.numel(),
+              lambda: _l.load().vgen_group_norm(_p(x), _p(out), n, p, c, _p(gamma), _p(beta), float(eps), 1 if silu else 0,
+                                                _p(ws), _stream()))
     _l.check(rc, "vgen_group_norm")
     return out
 
@@ -183,7 +224,8 @@ def layer_norm(x, gamma, beta, eps=1e-5, out=None):
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
-    rc = _l.load().vgen_layer_norm(_p(x2), _p(o2), rows, c, ldx, ldo, _p(gamma), _p(beta), float(eps), _stream())
+    rc = _run("layer_norm", 0.0, 4.0 * rows * c,
+              lambda: _l.load().vgen_layer_norm(_p(x2), _p(o2), rows, c, ldx, ldo, _p(gamma), _p(beta), float(eps), _stream()))
     _l.check(rc, "vgen_layer_norm")
     return out
 
@@ -203,8 +245,9 @@ def attention_d64(q, k, v, heads, kv_batch_div=1, out=None):
         raise _l.VgenError("attention_d64: shape mismatch")
     if out is None:
         out = torch.empty(b, lq, inner, device=q.device, dtype=torch.float16)
-    rc = _l.load().vgen_attention_d64(_p(q), _p(k), _p(v), _p(out), b, heads, lq, lk, q.stride(1), k.stride(1),
-                                      v.stride(1), out.stride(1), kv_batch_div, 64 ** -0.5, _stream())
+    rc = _run("attention_d64", 4.0 * b * heads * lq * lk * 64, 2.0 * (2 * b * lq * inner + 2 * k.shape[0] * lk * inner),
+              lambda: _l.load().vgen_attention_d64(_p(q), _p(k), _p(v), _p(out), b, heads, lq, lk, q.stride(1), k.stride(1),
+                                                   v.stride(1), out.stride(1), kv_batch_div, 64 ** -0.5, _stream()))
     _l.check(rc, "vgen_attention_d64")
     return out
 
@@ -222,8 +265,9 @@ def attention_temporal(q, k, v, heads, head_dim, out=None):
         raise _l.VgenError("attention_temporal: q/k/v must share strides")
     if out is None:
         out = torch.empty(f, npix, inner, device=q.device, dtype=torch.float16)
-    rc = _l.load().vgen_attention_temporal(_p(q), _p(k), _p(v), _p(out), npix, heads, f, head_dim, q.stride(0), q.stride(1),
-                                           out.stride(0), out.stride(1), head_dim ** -0.5, _stream())
+    rc = _run("attention_temporal", 4.0 * npix * heads * f * f * head_dim, 2.0 * 4 * f * npix * inner,
+              lambda: _l.load().vgen_attention_temporal(_p(q), _p(k), _p(v), _p(out), npix, heads, f, head_dim, q.stride(0),
+                                                        q.stride(1), out.stride(0), out.stride(1), head_dim ** -0.5, _stream()))
     _l.check(rc, "vgen_attention_temporal")
     return out
 
