@@ -32,7 +32,8 @@ int vgen_abi_version(void);
 const char* vgen_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t vgen_launch_count(void);
-/* 0 = tcgen05/TMA kernels (default), 1 = SIMT cross-check kernels for the tap-GEMM family (debug only). */
+/* tap-GEMM implementation: 0 = auto (default: tcgen05 CTA pairs, single CTA for one-tile problems),
+ * 1 = SIMT cross-check kernel (debug), 2 = force 1-CTA tcgen05, 3 = force 2-CTA (cta_group::2) tcgen05. */
 int vgen_set_tapgemm_impl(int impl);
 
 /* ---- tap-GEMM family (tcgen05.mma + TMA; tapgemm_sm100.cu) ------------------------------------ */

@@ -157,6 +157,14 @@ def group_tapgemm_simt():
     group_tapgemm("simt")
 
 
+def group_tapgemm_1cta():
+    group_tapgemm("1cta")
+
+
+def group_tapgemm_2cta():
+    group_tapgemm("2cta")
+
+
 def group_norm_checks():
     from vgen_b200 import ops
     F = torch.nn.functional
@@ -363,6 +371,8 @@ def group_elementwise():
 GROUPS = {
     "tapgemm": group_tapgemm,
     "tapgemm_simt": group_tapgemm_simt,
+    "tapgemm_1cta": group_tapgemm_1cta,
+    "tapgemm_2cta": group_tapgemm_2cta,
     "norm": group_norm_checks,
     "attention": group_attention,
     "elementwise": group_elementwise,

@@ -5,7 +5,7 @@
 
 namespace vg {
 
-static int g_tapgemm_impl = 0;  // 0 = sm100 (tcgen05), 1 = simt
+static int g_tapgemm_impl = 0;  // 0 = auto (CTA pairs when there are >= 2 M-tiles), 1 = simt, 2 = 1-CTA tcgen05, 3 = 2-CTA tcgen05
 
 static int pick_bn(long n, int geglu) {
   if (geglu) {
@@ -78,7 +78,9 @@ static int finish_and_launch(TapGemmArgs* t, const vgen_epilogue* epi, void* str
   if (tiles == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (g_tapgemm_impl == 1 || (s.c % 64) != 0) return tapgemm_simt_launch(*t, st);
-  return tapgemm_sm100_launch(*t, st);
+  const long m_tiles = (long)s.d3 * s.t2 * s.t1;
+  const bool pair = g_tapgemm_impl == 3 || (g_tapgemm_impl == 0 && m_tiles >= 2);
+  return pair ? tapgemm_sm100_2cta_launch(*t, st) : tapgemm_sm100_launch(*t, st);
 }
 
 }  // namespace vg
@@ -88,7 +90,7 @@ using namespace vg;
 extern "C" {
 
 int vgen_set_tapgemm_impl(int impl) {
-  if (impl != 0 && impl != 1) return fail("vgen_set_tapgemm_impl: impl must be 0 (sm100) or 1 (simt)");
+  if (impl < 0 || impl > 3) return fail("vgen_set_tapgemm_impl: impl must be 0 (auto), 1 (simt), 2 (1-CTA) or 3 (2-CTA)");
   g_tapgemm_impl = impl;
   return 0;
 }

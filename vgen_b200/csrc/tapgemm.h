@@ -42,7 +42,8 @@ struct TapGemmArgs {
   TapGemmEpilogue epi;
 };
 
-int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream);  // tcgen05 + TMA
+int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream);       // tcgen05 + TMA, one CTA per tile
+int tapgemm_sm100_2cta_launch(const TapGemmArgs& a, cudaStream_t stream);  // tcgen05 cta_group::2, CTA pair per 256-row tile
 int tapgemm_simt_launch(const TapGemmArgs& a, cudaStream_t stream);   // plain SIMT cross-check kernel
 
 }  // namespace vg

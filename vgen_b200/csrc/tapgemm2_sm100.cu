@@ -1,0 +1,228 @@
+// tapgemm, CTA-pair variant (tcgen05 cta_group::2): same maths and epilogue as tapgemm_sm100.cu, but two
+// CTAs of a cluster (the two SMs of a TPC) compute a 256 x BN tile together.  Each CTA stages its own 128
+// rows of A and only HALF of the W tile; the leader's single tcgen05.mma.cta_group::2 reads both CTAs'
+// shared memory.  Per FLOP this moves (128*64 + BN/2*64) instead of (128*64 + BN*64) operand elements
+// L2 -> SM per CTA, which is what bounds the 1-CTA kernel (profiles/r01a_ncu_summary.md).
+//
+//   warp 0 (both CTAs)   TMA producer: own A box + own half of W, completion signalled on the LEADER's
+//                        full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1 (leader only) MMA issuer: M = 256, commits multicast to both CTAs' empty / accumulator-full barriers
+//   warps 2-5 (both)     epilogue on the CTA's own 128 accumulator rows (its own TMEM)
+#include "common.h"
+#include "ptx.cuh"
+#include "tapgemm.h"
+#include "tapgemm_epilogue.cuh"
+
+namespace vg {
+
+static constexpr int kBM2 = 128;       // rows per CTA (UMMA M = 256 per pair)
+static constexpr int kBK2 = 64;
+static constexpr int kThreads2 = 192;
+static constexpr uint32_t kTmemCols2 = 512;
+static constexpr int kABytes2 = kBM2 * kBK2 * 2;
+
+struct alignas(64) TapGemm2Params {
+  CUtensorMap map_a;
+  CUtensorMap map_b;     // box {64, BN/2}
+  TapGemmShape s;
+  TapGemmEpilogue e;
+  int stages;
+  int b_slot_bytes;
+  int m_tiles;           // d3 * t2 * t1
+  int total_pair_tiles;  // ceil(m_tiles / 2) * nb
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+    tapgemm_sm100_2cta_kernel(const __grid_constant__ TapGemm2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int stages = p.stages;
+  const int stage_bytes = kABytes2 + p.b_slot_bytes;
+
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* full_bar = bars;                      // [stages]  (the leader's copy is the one in use)
+  uint64_t* empty_bar = bars + stages;            // [stages]  local, arrived by the multicast commit
+  uint64_t* tfull_bar = bars + 2 * stages;        // [2]       local, arrived by the multicast commit
+  uint64_t* tempty_bar = bars + 2 * stages + 2;   // [2]       the leader's copy collects 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const TapGemmShape& s = p.s;
+  const int k_iters = s.num_taps * s.kc;
+  const int BN = s.bn;
+  const int half_n = BN >> 1;
+  const uint32_t stage_tx = (uint32_t)(s.box1 * s.box2 * kBK2 * 2 + half_n * kBK2 * 2);  // bytes landing in ONE CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm<kTmemCols2>(tmem_slot);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t it_g = 0;
+      for (int pt = cluster_id; pt < p.total_pair_tiles; pt += num_clusters) {
+        const int nb_i = pt % s.nb;
+        const int m = 2 * (pt / s.nb) + (int)rank;   // this CTA's M-tile (may be one past the end: loads zeros)
+        const int t1_i = m % s.t1;
+        const int rest = m / s.t1;
+        const int t2_i = rest % s.t2;
+        const int i3 = rest / s.t2;
+        const int i1_0 = t1_i * s.box1, i2_0 = t2_i * s.box2;
+        const int n0 = nb_i * BN + (int)rank * half_n;
+        for (int it = 0; it < k_iters; ++it, ++it_g) {
+          const int st = it_g % stages;
+          const uint32_t ph = (it_g / stages) & 1;
+          const int tap = it / s.kc;
+          const int c0 = (it - tap * s.kc) * kBK2;
+          mbar_wait(&empty_bar[st], ph ^ 1, 31);
+          if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * stage_tx);
+          const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[st]), 0);
+          uint8_t* sa = tiles + (size_t)st * stage_bytes;
+          tma_load_4d_2sm(sa, &p.map_a, full_leader, c0, i1_0 + s.tap1[tap], i2_0 + s.tap2[tap], i3 + s.tap3[tap]);
+          tma_load_2d_2sm(sa + kABytes2, &p.map_b, full_leader, tap * s.c + c0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(2 * kBM2, BN, 0, 0);
+      uint32_t it_g = 0;
+      uint32_t lt = 0;
+      for (int pt = cluster_id; pt < p.total_pair_tiles; pt += num_clusters, ++lt) {
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1, 32);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int it = 0; it < k_iters; ++it, ++it_g) {
+          const int st = it_g % stages;
+          const uint32_t ph = (it_g / stages) & 1;
+          mbar_wait(&full_bar[st], ph, 33);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + (size_t)st * stage_bytes);
+          const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes2, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK2 / 16; ++k)
+            umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[st], 3);     // frees the stage in BOTH CTAs
+        }
+        umma_commit_2sm(&tfull_bar[as], 3);       // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    const TapGemmEpilogue& e = p.e;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int rows_in_tile = s.box1 * s.box2;
+    const int out_n = e.geglu ? (s.n >> 1) : s.n;
+    const bool vec_ok = tapgemm_vec_ok(e, out_n);
+    uint32_t lt = 0;
+    for (int pt = cluster_id; pt < p.total_pair_tiles; pt += num_clusters, ++lt) {
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      EpiRow t;
+      t.nb_i = pt % s.nb;
+      const int m = 2 * (pt / s.nb) + (int)rank;
+      const int t1_i = m % s.t1;
+      const int rest = m / s.t1;
+      const int t2_i = rest % s.t2;
+      t.i3 = rest / s.t2;
+      const int i1 = t1_i * s.box1 + (r % s.box1);
+      const int i2 = t2_i * s.box2 + (r / s.box1);
+      t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2) && (t.i3 < s.d3);
+      t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
+      mbar_wait(&tfull_bar[as], aph, 34);
+      tc_fence_after();
+      t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<kTmemCols2>(tmem_base);
+  }
+}
+
+int tapgemm_sm100_2cta_launch(const TapGemmArgs& a, cudaStream_t stream) {
+  const TapGemmShape& s = a.shape;
+  VG_REQUIRE(s.c % 64 == 0, "tapgemm_2cta: C must be a multiple of 64");
+  VG_REQUIRE(s.bn >= 32 && s.bn <= 256 && s.bn % 32 == 0, "tapgemm_2cta: BN must be in [32,256], multiple of 32");
+  VG_REQUIRE(s.box1 >= 1 && s.box2 >= 1 && s.box1 * s.box2 <= kBM2 && s.box1 <= 256 && s.box2 <= 256, "tapgemm_2cta: bad box");
+  VG_REQUIRE(s.num_taps >= 1 && s.num_taps <= kMaxTaps, "tapgemm_2cta: bad tap count");
+  VG_REQUIRE((reinterpret_cast<uintptr_t>(a.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0,
+             "tapgemm_2cta: A and W must be 16-byte aligned");
+  if (a.epi.geglu) VG_REQUIRE(s.bn % 64 == 0 && s.n % s.bn == 0, "tapgemm_2cta: GEGLU needs BN%64==0 and N%BN==0");
+
+  TapGemm2Params p;
+  p.s = s;
+  p.e = a.epi;
+  {
+    const uint64_t dims[4] = {(uint64_t)s.c, (uint64_t)s.d1, (uint64_t)s.d2, (uint64_t)s.d3};
+    const uint64_t strides[3] = {(uint64_t)a.a_stride1 * 2, (uint64_t)a.a_stride2 * 2, (uint64_t)a.a_stride3 * 2};
+    const uint32_t box[4] = {64, (uint32_t)s.box1, (uint32_t)s.box2, 1};
+    int rc = make_tmap_f16(&p.map_a, a.a, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)s.num_taps * s.c, (uint64_t)s.n};
+    const uint64_t strides[1] = {(uint64_t)s.num_taps * s.c * 2};
+    const uint32_t box[2] = {64, (uint32_t)(s.bn / 2)};
+    int rc = make_tmap_f16(&p.map_b, a.w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  p.b_slot_bytes = (((s.bn / 2) * kBK2 * 2 + 1023) / 1024) * 1024;
+  const int stage_bytes = kABytes2 + p.b_slot_bytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.m_tiles = s.d3 * s.t2 * s.t1;
+  p.total_pair_tiles = ((p.m_tiles + 1) / 2) * s.nb;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  int clusters = sm_count() / 2;
+  if (clusters > p.total_pair_tiles) clusters = p.total_pair_tiles;
+  if (clusters < 1) return 0;
+  tapgemm_sm100_2cta_kernel<<<2 * clusters, kThreads2, smem, stream>>>(p);
+  VG_LAUNCH_CHECK("tapgemm_sm100_2cta_kernel");
+  return 0;
+}
+
+}  // namespace vg

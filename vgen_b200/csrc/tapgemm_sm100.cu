@@ -24,6 +24,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include "tapgemm.h"
+#include "tapgemm_epilogue.cuh"
 
 namespace vg {
 
@@ -41,8 +42,6 @@ struct alignas(64) TapGemmKernelParams {
   int stages;
   int b_slot_bytes;  // smem bytes reserved per stage for the W tile (>= BN*128, multiple of 1024)
 };
-
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid_constant__ TapGemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -150,126 +149,26 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
     const int r = q * 32 + lane;
     const int rows_in_tile = s.box1 * s.box2;
     const int out_n = e.geglu ? (s.n >> 1) : s.n;
-    const bool vec_ok = ((e.ldo & 7) == 0) && ((out_n & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0) &&
-                        (e.residual == nullptr ||
-                         (((e.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0)));
+    const bool vec_ok = tapgemm_vec_ok(e, out_n);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-      int nb_i = tile % s.nb;
+      EpiRow t;
+      t.nb_i = tile % s.nb;
       int rest = tile / s.nb;
       const int t1_i = rest % s.t1;
       rest /= s.t1;
       const int t2_i = rest % s.t2;
-      const int i3 = rest / s.t2;
+      t.i3 = rest / s.t2;
       const int i1 = t1_i * s.box1 + (r % s.box1);
       const int i2 = t2_i * s.box2 + (r / s.box1);
-      const bool row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
-      const long row = ((long)i3 * s.d2 + i2) * s.d1 + i1;
+      t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
+      t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
 
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-
-      if (!e.geglu) {
-        const int n0 = nb_i * BN;
-        __half* orow = e.out + row * e.ldo;
-        const __half* rrow = e.residual ? e.residual + row * e.ldr : nullptr;
-        const __half* grow = e.group_bias ? e.group_bias + (long)(i3 / e.group_bias_div) * e.ld_group_bias : nullptr;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-          const int nbase = n0 + c0;
-          if (nbase >= s.n) continue;
-          if (vec_ok && nbase + 32 <= s.n) {
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a = __uint_as_float(v[j8 * 8 + j]) * e.alpha;
-                if (e.bias) a += __ldg(e.bias + nbase + j8 * 8 + j);
-                f[j] = a;
-              }
-              if (grow) {
-                // reference: h (fp16 conv output) + emb_out (fp16) -> fp16  (util.py:909-919)
-                const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(grow + nbase + j8 * 8));
-                const __half* gh = reinterpret_cast<const __half*>(&g4);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __half2float(__float2half_rn(f[j])) + __half2float(gh[j]);
-              }
-              if (rrow) {
-                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + nbase + j8 * 8));
-                const __half* rh = reinterpret_cast<const __half*>(&r4);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __half2float(__float2half_rn(f[j])) + __half2float(rh[j]);
-              }
-              uint4 o;
-              o.x = pack_half2(f[0], f[1]);
-              o.y = pack_half2(f[2], f[3]);
-              o.z = pack_half2(f[4], f[5]);
-              o.w = pack_half2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(orow + nbase + j8 * 8) = o;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j) {
-              const int n = nbase + j;
-              if (n >= s.n) break;
-              float a = __uint_as_float(v[j]) * e.alpha;
-              if (e.bias) a += e.bias[n];
-              if (grow) a = __half2float(__float2half_rn(a)) + __half2float(grow[n]);
-              if (rrow) a = __half2float(__float2half_rn(a)) + __half2float(rrow[n]);
-              orow[n] = __float2half_rn(a);
-            }
-          }
-        }
-      } else {
-        // GEGLU: columns [0,BN/2) of this tile are "value" j, columns [BN/2,BN) the matching "gate" j
-        // (host interleaves the weight rows per BN block).  out = value * gelu(gate)   (util.py:707-714)
-        const int hb = BN >> 1;
-        const int o0 = nb_i * hb;
-        __half* orow = e.out + row * e.ldo;
-        for (int c0 = 0; c0 < hb; c0 += 32) {
-          uint32_t v[32], g[32];
-          tmem_ld32(t_row + c0, v);
-          tmem_ld32(t_row + hb + c0, g);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-          const int obase = o0 + c0;
-          if (obase >= out_n) continue;
-          const int wbase = nb_i * BN + c0;  // packed weight-row index of value j (gate is + hb)
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]) * e.alpha;
-            float b = __uint_as_float(g[j]) * e.alpha;
-            if (e.bias) {
-              a += __ldg(e.bias + wbase + j);
-              b += __ldg(e.bias + wbase + hb + j);
-            }
-            // reference rounds the projection to fp16, gelu to fp16, product to fp16
-            const float a16 = __half2float(__float2half_rn(a));
-            const float b16 = __half2float(__float2half_rn(b));
-            const float ge = __half2float(__float2half_rn(gelu_erf(b16)));
-            f[j] = a16 * ge;
-          }
-          if (vec_ok && obase + 32 <= out_n) {
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              uint4 o;
-              o.x = pack_half2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-              o.y = pack_half2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-              o.z = pack_half2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-              o.w = pack_half2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(orow + obase + j8 * 8) = o;
-            }
-          } else {
-            for (int j = 0; j < 32 && obase + j < out_n; ++j) orow[obase + j] = __float2half_rn(f[j]);
-          }
-        }
-      }
+      t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n);
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();

@@ -161,7 +161,7 @@ def tconv3(x, w, bias=None, residual=None, out=None, bn=0):
 
 
 def set_tapgemm_impl(impl: str):
-    _l.check(_l.load().vgen_set_tapgemm_impl({"sm100": 0, "simt": 1}[impl]), "vgen_set_tapgemm_impl")
+    _l.check(_l.load().vgen_set_tapgemm_impl({"auto": 0, "sm100": 0, "simt": 1, "1cta": 2, "2cta": 3}[impl]), "vgen_set_tapgemm_impl")
 
 
 def pack_geglu_weight(w, bias, bn):
