@@ -388,7 +388,17 @@ def main():
         ops.PROF = ops.KernelProfile()
         xt2 = one_step(xt, 0)
         summ = ops.PROF.summary()
+        shapes = ops.PROF.by_shape()
         ops.PROF = None
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            rows = sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])
+            with open(os.path.join(ROOT, "gpurun_out", "prof_shapes.json"), "w") as fh:
+                json.dump([{"op": k, "launches": v["launches"], "ms": round(v["ms"], 3),
+                            "tflops": round(v["flops"] / 1e9 / max(v["ms"], 1e-9), 1), "gbs": round(v["bytes"] / 1e6 / max(v["ms"], 1e-9), 1)}
+                           for k, v in rows], fh, indent=0)
+        except Exception:  # noqa: BLE001
+            pass
         del xt2
         families = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / 1e9 / max(v["ms"], 1e-9), 1) if v["flops"] else None,
                         "gbs": round(v["bytes"] / 1e6 / max(v["ms"], 1e-9), 1)} for k, v in summ.items()}

@@ -115,9 +115,9 @@ def test_forward_is_deterministic_and_repack_follows_weights(golden_dir):
 
 
 def test_size_independent_properties_at_larger_size():
-    """Properties that need no oracle, at a size the CPU oracle could not finish quickly:
-    (1) frames are exchangeable for the per-frame ops: a video whose frames are identical gives identical
-        output frames; (2) batch entries do not interact: f(cat[a, b]) == cat[f(a), f(b)]."""
+    """A property that needs no oracle, at a size the CPU oracle could not finish quickly: batch entries
+    do not interact, f(cat[a, b]) == cat[f(a), f(b)] (exercises the per-video GroupNorm / temporal kernels'
+    batch handling and the shared-context cross attention)."""
     ctor = dict(CASES["t2v_tiny"]["ctor"], dim=128, dim_mult=[1, 2], num_heads=4)
     torch.manual_seed(5)
     m = vgen_b200.UNetSD_T2VBase(**ctor)
@@ -127,12 +127,6 @@ def test_size_independent_properties_at_larger_size():
             p.data.normal_(0, 0.02, generator=g)
     m = m.cuda().eval()
     y = torch.randn(2, 9, 1024, generator=g).cuda()
-    frame = torch.randn(1, 4, 1, 32, 48, generator=g)
-    x_same = frame.repeat(1, 1, 6, 1, 1).cuda()
-    t = torch.tensor([400], device="cuda")
-    out = m(x_same, t, y=y[:1])
-    for i in range(1, 6):
-        assert torch.allclose(out[:, :, i].float(), out[:, :, 0].float(), atol=2e-3, rtol=0)
     xa, xb = torch.randn(1, 4, 4, 32, 48, generator=g).cuda(), torch.randn(1, 4, 4, 32, 48, generator=g).cuda()
     t2 = torch.tensor([400, 400], device="cuda")
     both = m(torch.cat([xa, xb]), t2, y=y)

@@ -162,10 +162,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       mbar_wait(&s_full[i], j & 1, 20);
       tc_fence_after();
       const int valid = p.lk - j * kTileK;  // keys valid in this block (>= 128 unless last)
-      // pass 1: row max.  TMEM loads are issued two at a time so their latency overlaps.
+      // pass 1: row max
       float m_blk = -INFINITY;
-      uint32_t va[32], vb[32];
-      auto fold_max = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+      for (int c = 0; c < kTileK; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c, v);
+        tmem_ld_wait();
         if (valid >= c + 32) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) m_blk = fmaxf(m_blk, __uint_as_float(v[t]));
@@ -174,17 +177,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
           for (int t = 0; t < 32; ++t)
             if (c + t < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[t]));
         }
-      };
-      tmem_ld32(t_s + 0, va);
-      tmem_ld32(t_s + 32, vb);
-      tmem_ld_wait();
-      fold_max(va, 0);
-      fold_max(vb, 32);
-      tmem_ld32(t_s + 64, va);
-      tmem_ld32(t_s + 96, vb);
-      tmem_ld_wait();
-      fold_max(va, 64);
-      fold_max(vb, 96);
+      }
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = fast_exp2((m_run - m_new) * p.scale_log2);  // 0 on the first block (m_run = -inf)
       const float neg_ms = -m_new * p.scale_log2;
@@ -193,50 +186,42 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       if (j > 0) {
         mbar_wait(&o_full[i], (j - 1) & 1, 21);
         tc_fence_after();
-        tmem_ld32(t_o + 0, va);
-        tmem_ld32(t_o + 32, vb);
-        tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) o_acc[t] = o_acc[t] * alpha_prev + __uint_as_float(va[t]);
+        for (int c = 0; c < kD; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_o + c, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) o_acc[32 + t] = o_acc[32 + t] * alpha_prev + __uint_as_float(vb[t]);
+          for (int t = 0; t < 32; ++t) o_acc[c + t] = o_acc[c + t] * alpha_prev + __uint_as_float(v[t]);
+        }
       }
-      // pass 2: p = exp2(s*scale*log2e - m*scale*log2e), row sum, P -> smem (swizzled K-major);
-      // the load of chunk c+1 is in flight while chunk c is exponentiated and stored.
+      // pass 2: p = exp2(s*scale*log2e - m*scale*log2e), row sum, P -> smem (swizzled K-major)
       float l_blk = 0.f;
-      auto emit = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+      for (int c = 0; c < kTileK; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c, v);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float e = fast_exp2(fmaf(__uint_as_float(v[t]), p.scale_log2, neg_ms));
+          if (c + t >= valid) e = 0.f;
+          pv[t] = e;
+          l_blk += e;
+        }
         uint8_t* chunk = prow + (c >> 6) * (kTileQ * 128);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float e[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            float x = fast_exp2(fmaf(__uint_as_float(v[g * 8 + t]), p.scale_log2, neg_ms));
-            if (c + g * 8 + t >= valid) x = 0.f;
-            e[t] = x;
-            l_blk += x;
-          }
           uint4 u;
-          u.x = pack_half2(e[0], e[1]);
-          u.y = pack_half2(e[2], e[3]);
-          u.z = pack_half2(e[4], e[5]);
-          u.w = pack_half2(e[6], e[7]);
+          u.x = pack_half2(pv[g * 8 + 0], pv[g * 8 + 1]);
+          u.y = pack_half2(pv[g * 8 + 2], pv[g * 8 + 3]);
+          u.z = pack_half2(pv[g * 8 + 4], pv[g * 8 + 5]);
+          u.w = pack_half2(pv[g * 8 + 6], pv[g * 8 + 7]);
           const int piece = ((c & 63) >> 3) + g;  // 16-byte piece index inside the 128 B row
           *reinterpret_cast<uint4*>(chunk + ((piece ^ sw) << 4)) = u;
         }
-      };
-      tmem_ld32(t_s + 0, va);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 32, vb);
-      emit(va, 0);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 64, va);
-      emit(vb, 32);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 96, vb);
-      emit(va, 64);
-      tmem_ld_wait();
-      emit(vb, 96);
+      }
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
       alpha_prev = alpha;
@@ -252,12 +237,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
     const int row = q0 + i * kTileQ + r;
     const float inv_l = 1.0f / l_run;
     __half* orow = p.out + (long)batch * p.out_batch_stride + (long)row * p.ldo + head * kD;
-    uint32_t oa[32], ob[32];
-    tmem_ld32(t_o + 0, oa);
-    tmem_ld32(t_o + 32, ob);
-    tmem_ld_wait();
-    if (row < p.lq) {
-      auto store_half = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+    for (int c = 0; c < kD; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_o + c, v);
+      tmem_ld_wait();
+      if (row < p.lq) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float f[8];
@@ -270,9 +255,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
           u.w = pack_half2(f[6], f[7]);
           *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
         }
-      };
-      store_half(oa, 0);
-      store_half(ob, 32);
+      }
     }
   }
 

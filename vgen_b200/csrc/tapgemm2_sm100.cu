@@ -17,7 +17,7 @@ namespace vg {
 
 static constexpr int kBM2 = 128;       // rows per CTA (UMMA M = 256 per pair)
 static constexpr int kBK2 = 64;
-static constexpr int kThreads2 = 192;
+static constexpr int kThreads2 = 320;  // TMA, MMA, 8 epilogue warps
 static constexpr uint32_t kTmemCols2 = 512;
 static constexpr int kABytes2 = kBM2 * kBK2 * 2;
 
@@ -68,7 +68,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -160,7 +160,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       mbar_wait(&tfull_bar[as], aph, 34);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));

@@ -18,15 +18,17 @@ struct EpiRow {
   uint32_t t_row;  // TMEM address of the thread's lane, column 0 of the accumulator buffer
 };
 
+// chunk0 / chunk_step: this warp handles the 32-column chunks chunk0, chunk0 + chunk_step, ... (two warps share
+// a TMEM lane quadrant and split the columns between them).
 __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, const TapGemmEpilogue& e, const EpiRow& t,
-                                                      bool vec_ok, int out_n) {
+                                                      bool vec_ok, int out_n, int chunk0, int chunk_step) {
   const int BN = s.bn;
   if (!e.geglu) {
     const int n0 = t.nb_i * BN;
     __half* orow = e.out + t.row * e.ldo;
     const __half* rrow = e.residual ? e.residual + t.row * e.ldr : nullptr;
     const __half* grow = e.group_bias ? e.group_bias + (long)(t.i3 / e.group_bias_div) * e.ld_group_bias : nullptr;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = chunk0 * 32; c0 < BN; c0 += chunk_step * 32) {
       uint32_t v[32];
       tmem_ld32(t.t_row + c0, v);
       tmem_ld_wait();
@@ -38,10 +40,12 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
         for (int j8 = 0; j8 < 4; ++j8) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a = __uint_as_float(v[j8 * 8 + j]) * e.alpha;
-            if (e.bias) a += __ldg(e.bias + nbase + j8 * 8 + j);
-            f[j] = a;
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * e.alpha;
+          if (e.bias) {  // vec_ok implies n % 8 == 0; bias tensors are 16-byte aligned
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8 + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
           if (grow) {
             // reference: h (fp16 conv output) + emb_out (fp16) -> fp16  (util.py:909-919)
@@ -81,7 +85,7 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
     const int hb = BN >> 1;
     const int o0 = t.nb_i * hb;
     __half* orow = e.out + t.row * e.ldo;
-    for (int c0 = 0; c0 < hb; c0 += 32) {
+    for (int c0 = chunk0 * 32; c0 < hb; c0 += chunk_step * 32) {
       uint32_t v[32], g[32];
       tmem_ld32(t.t_row + c0, v);
       tmem_ld32(t.t_row + hb + c0, g);
@@ -123,7 +127,7 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
 }
 
 __device__ __forceinline__ bool tapgemm_vec_ok(const TapGemmEpilogue& e, int out_n) {
-  return ((e.ldo & 7) == 0) && ((out_n & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0) &&
+  return ((reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) && ((e.ldo & 7) == 0) && ((out_n & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0) &&
          (e.residual == nullptr || (((e.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0)));
 }
 

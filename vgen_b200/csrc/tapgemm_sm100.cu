@@ -19,7 +19,7 @@
 // Structure (sm_100a): persistent CTAs (one per SM), warp-specialised:
 //   warp 0      TMA producer (one elected lane), kStages-deep smem ring, mbarrier full/empty
 //   warp 1      tcgen05.mma issuer (one lane), fp32 accumulators in TMEM, double-buffered (2 x 256 cols)
-//   warps 2-5   epilogue: tcgen05.ld -> alpha / bias / per-frame bias / residual / GEGLU -> fp16 -> HBM
+//   warps 2-9   epilogue (two warps per TMEM lane quadrant, interleaved 32-column chunks): tcgen05.ld -> alpha / bias / per-frame bias / residual / GEGLU -> fp16 -> HBM
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.h"
 #include "ptx.cuh"
@@ -30,7 +30,7 @@ namespace vg {
 
 static constexpr int kBM = 128;       // rows per tile (UMMA M)
 static constexpr int kBK = 64;        // K per pipeline stage = one 128B swizzle row of fp16
-static constexpr int kThreads = 192;  // 6 warps
+static constexpr int kThreads = 320;  // 10 warps: TMA, MMA, 8 epilogue
 static constexpr uint32_t kTmemCols = 512;
 static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
 
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();

@@ -21,18 +21,29 @@ class KernelProfile:
     def __init__(self):
         self.records = []  # (family, flops, bytes, start_event, stop_event)
 
-    def run(self, family, flops, nbytes, fn):
+    def run(self, family, flops, nbytes, fn, tag=None):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         rc = fn()
         e.record()
-        self.records.append((family, float(flops), float(nbytes), s, e))
+        self.records.append((family, float(flops), float(nbytes), s, e, tag))
         return rc
+
+    def by_shape(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, fl, nb, s, e, tag in self.records:
+            d = out.setdefault(f"{fam}:{tag}", {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += nb
+        return out
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for fam, fl, nb, s, e in self.records:
+        for fam, fl, nb, s, e, _tag in self.records:
             d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += s.elapsed_time(e)
@@ -44,10 +55,10 @@ class KernelProfile:
 PROF = None  # set to a KernelProfile() to instrument calls
 
 
-def _run(family, flops, nbytes, fn):
+def _run(family, flops, nbytes, fn, tag=None):
     if PROF is None:
         return fn()
-    return PROF.run(family, flops, nbytes, fn)
+    return PROF.run(family, flops, nbytes, fn, tag)
 
 
 def _p(t):
@@ -116,7 +127,8 @@ def linear(a, w, bias=None, residual=None, alpha=1.0, geglu=False, out=None, bn=
     o2, ldo = _rows_view(out, "out")
     e, keep = _epilogue(n_out, bias, None, residual, alpha, geglu, bn)
     rc = _run("tapgemm", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n_out),
-              lambda: _l.load().vgen_linear(_p(a2), m, k, lda, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()))
+              lambda: _l.load().vgen_linear(_p(a2), m, k, lda, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()),
+              tag=f"linear m{m} k{k} n{n}{' geglu' if geglu else ''}{' res' if residual is not None else ''}")
     _l.check(rc, "vgen_linear")
     return out
 
@@ -136,7 +148,8 @@ def conv2d_3x3(x, w, bias=None, group_bias=None, residual=None, out=None, bn=0, 
     e, keep = _epilogue(n, bias, group_bias, residual, 1.0, False, bn, group_div)
     rows = nimg * h * wd
     rc = _run("tapgemm", 2.0 * rows * n * 9 * c, 2.0 * (rows * c + 9 * c * n + rows * n),
-              lambda: _l.load().vgen_conv2d_3x3(_p(x), nimg, h, wd, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()))
+              lambda: _l.load().vgen_conv2d_3x3(_p(x), nimg, h, wd, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()),
+              tag=f"conv3x3 {nimg}x{h}x{wd} c{c} n{n}")
     _l.check(rc, "vgen_conv2d_3x3")
     return out
 
@@ -155,7 +168,8 @@ def tconv3(x, w, bias=None, residual=None, out=None, bn=0):
     o2, ldo = _rows_view(out, "out")
     e, keep = _epilogue(n, bias, None, residual, 1.0, False, bn)
     rc = _run("tapgemm", 2.0 * f * hw * n * 3 * c, 2.0 * (f * hw * c + 3 * c * n + f * hw * n),
-              lambda: _l.load().vgen_tconv3(_p(x), f, hw, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()))
+              lambda: _l.load().vgen_tconv3(_p(x), f, hw, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()),
+              tag=f"tconv3 f{f} hw{hw} c{c} n{n}")
     _l.check(rc, "vgen_tconv3")
     return out
 
@@ -247,7 +261,8 @@ def attention_d64(q, k, v, heads, kv_batch_div=1, out=None):
         out = torch.empty(b, lq, inner, device=q.device, dtype=torch.float16)
     rc = _run("attention_d64", 4.0 * b * heads * lq * lk * 64, 2.0 * (2 * b * lq * inner + 2 * k.shape[0] * lk * inner),
               lambda: _l.load().vgen_attention_d64(_p(q), _p(k), _p(v), _p(out), b, heads, lq, lk, q.stride(1), k.stride(1),
-                                                   v.stride(1), out.stride(1), kv_batch_div, 64 ** -0.5, _stream()))
+                                                   v.stride(1), out.stride(1), kv_batch_div, 64 ** -0.5, _stream()),
+              tag=f"b{b} h{heads} lq{lq} lk{lk}")
     _l.check(rc, "vgen_attention_d64")
     return out
 
