@@ -430,6 +430,8 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     parallel.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return 0
 
 

@@ -1,5 +1,7 @@
 // C-ABI entry points of the tap-GEMM family: they only describe the problem (extents, taps, tile
 // shape) and hand it to the tcgen05 kernel (or, for debugging, the SIMT cross-check kernel).
+#include <stdlib.h>
+
 #include "common.h"
 #include "tapgemm.h"
 
@@ -60,10 +62,24 @@ static int fill_epilogue(TapGemmArgs* t, void* out, long ldo, const vgen_epilogu
   e.residual = epi ? reinterpret_cast<const __half*>(epi->residual) : nullptr;
   e.ldr = epi ? epi->residual_ld : 0;
   e.geglu = epi ? epi->geglu : 0;
+  {
+    static int staged = -1;  // VGEN_EPI_STAGED=1 selects the shared-memory transposing epilogue (A/B measurements)
+    if (staged < 0) {
+      const char* ev = getenv("VGEN_EPI_STAGED");
+      staged = (ev && ev[0] == '1') ? 1 : 0;
+    }
+    e.staged = staged;
+  }
   return 0;
 }
 
 static int finish_and_launch(TapGemmArgs* t, const vgen_epilogue* epi, void* stream) {
+  static bool env_read = false;
+  if (!env_read) {  // VGEN_TAPGEMM_IMPL=0..3 overrides the default once (A/B measurements)
+    env_read = true;
+    const char* ev = getenv("VGEN_TAPGEMM_IMPL");
+    if (ev && ev[0] >= '0' && ev[0] <= '3') g_tapgemm_impl = ev[0] - '0';
+  }
   TapGemmShape& s = t->shape;
   s.kc = s.c / 64;
   int bn = (epi && epi->bn > 0) ? epi->bn : pick_bn(s.n, t->epi.geglu);

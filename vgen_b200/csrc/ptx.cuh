@@ -58,6 +58,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// One lane of a fully-converged warp (elect.sync).  The single-thread tcgen05 / TMA instructions are issued
+// under this predicate while the WHOLE warp runs the surrounding loop, so their operands stay warp-uniform
+// (uniform registers) instead of going through per-instruction R2UR "waterfall" loops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- fences
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -52,6 +52,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
   uint64_t* tfull_bar = bars + 2 * stages;        // [2]       local, arrived by the multicast commit
   uint64_t* tempty_bar = bars + 2 * stages + 2;   // [2]       the leader's copy collects 8 warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars + 2 * stages + 6);  // 8 warps x kEpiStageBytes, 16B aligned
 
   const TapGemmShape& s = p.s;
   const int k_iters = s.num_taps * s.kc;
@@ -83,35 +84,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      uint32_t it_g = 0;
-      for (int pt = cluster_id; pt < p.total_pair_tiles; pt += num_clusters) {
-        const int nb_i = pt % s.nb;
-        const int m = 2 * (pt / s.nb) + (int)rank;   // this CTA's M-tile (may be one past the end: loads zeros)
-        const int t1_i = m % s.t1;
-        const int rest = m / s.t1;
-        const int t2_i = rest % s.t2;
-        const int i3 = rest / s.t2;
-        const int i1_0 = t1_i * s.box1, i2_0 = t2_i * s.box2;
-        const int n0 = nb_i * BN + (int)rank * half_n;
-        for (int it = 0; it < k_iters; ++it, ++it_g) {
-          const int st = it_g % stages;
-          const uint32_t ph = (it_g / stages) & 1;
-          const int tap = it / s.kc;
-          const int c0 = (it - tap * s.kc) * kBK2;
-          mbar_wait(&empty_bar[st], ph ^ 1, 31);
+    // the whole warp walks the loop (warp-uniform operands); one elected lane issues the TMA
+    uint32_t it_g = 0;
+    for (int pt = cluster_id; pt < p.total_pair_tiles; pt += num_clusters) {
+      const int nb_i = pt % s.nb;
+      const int m = 2 * (pt / s.nb) + (int)rank;   // this CTA's M-tile (may be one past the end: loads zeros)
+      const int t1_i = m % s.t1;
+      const int rest = m / s.t1;
+      const int t2_i = rest % s.t2;
+      const int i3 = rest / s.t2;
+      const int i1_0 = t1_i * s.box1, i2_0 = t2_i * s.box2;
+      const int n0 = nb_i * BN + (int)rank * half_n;
+      int tap = 0, kc_i = 0;
+      for (int it = 0; it < k_iters; ++it, ++it_g) {
+        const int st = it_g % stages;
+        const uint32_t ph = (it_g / stages) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1, 31);
+        if (elect_one()) {
           if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * stage_tx);
           const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[st]), 0);
           uint8_t* sa = tiles + (size_t)st * stage_bytes;
-          tma_load_4d_2sm(sa, &p.map_a, full_leader, c0, i1_0 + s.tap1[tap], i2_0 + s.tap2[tap], i3 + s.tap3[tap]);
-          tma_load_2d_2sm(sa + kABytes2, &p.map_b, full_leader, tap * s.c + c0, n0);
+          tma_load_4d_2sm(sa, &p.map_a, full_leader, kc_i * kBK2, i1_0 + s.tap1[tap], i2_0 + s.tap2[tap], i3 + s.tap3[tap]);
+          tma_load_2d_2sm(sa + kABytes2, &p.map_b, full_leader, tap * s.c + kc_i * kBK2, n0);
+        }
+        __syncwarp();
+        if (++kc_i == s.kc) {
+          kc_i = 0;
+          ++tap;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0 && lane == 0) {
+    // whole warp in the loop, one elected lane issues tcgen05.mma / commit
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_f16(2 * kBM2, BN, 0, 0);
+      const uint32_t tiles_addr = smem_u32(tiles);
       uint32_t it_g = 0;
       uint32_t lt = 0;
       for (int pt = cluster_id; pt < p.total_pair_tiles; pt += num_clusters, ++lt) {
@@ -124,15 +132,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
           const uint32_t ph = (it_g / stages) & 1;
           mbar_wait(&full_bar[st], ph, 33);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + (size_t)st * stage_bytes);
-          const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes2, 16, 1024);
+          if (elect_one()) {
+            const uint32_t a_addr = tiles_addr + (uint32_t)st * (uint32_t)stage_bytes;
+            const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
+            const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes2, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kBK2 / 16; ++k)
-            umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[st], 3);     // frees the stage in BOTH CTAs
+            for (int k = 0; k < kBK2 / 16; ++k)
+              umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[st], 3);                         // frees the stage in BOTH CTAs
+            if (it == k_iters - 1) umma_commit_2sm(&tfull_bar[as], 3);  // accumulator ready in BOTH CTAs
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(&tfull_bar[as], 3);       // accumulator ready in BOTH CTAs
       }
     }
   } else {
@@ -153,6 +164,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       const int rest = m / s.t1;
       const int t2_i = rest % s.t2;
       t.i3 = rest / s.t2;
+      t.t1_i = t1_i;
+      t.t2_i = t2_i;
+      t.q = q;
       const int i1 = t1_i * s.box1 + (r % s.box1);
       const int i2 = t2_i * s.box2 + (r / s.box1);
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2) && (t.i3 < s.d3);
@@ -160,7 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       mbar_wait(&tfull_bar[as], aph, 34);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2, epi_stage + (warp - 2) * kEpiStageBytes);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
@@ -204,13 +218,13 @@ int tapgemm_sm100_2cta_launch(const TapGemmArgs& a, cudaStream_t stream) {
   }
   p.b_slot_bytes = (((s.bn / 2) * kBK2 * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes2 + p.b_slot_bytes;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (226 * 1024 - kEpiWarps * kEpiStageBytes - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.m_tiles = s.d3 * s.t2 * s.t1;
   p.total_pair_tiles = ((p.m_tiles + 1) / 2) * s.nb;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + kEpiWarps * kEpiStageBytes + 1024;
 
   static bool attr_done = false;
   if (!attr_done) {

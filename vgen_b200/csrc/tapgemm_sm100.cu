@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
   uint64_t* tfull_bar = bars + 2 * stages;   // [2]
   uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars + 2 * stages + 6);  // 8 warps x kEpiStageBytes, 16B aligned
 
   const TapGemmShape& s = p.s;
   const int k_iters = s.num_taps * s.kc;
@@ -90,46 +91,53 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it_g = 0;
-      for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x) {
-        int nb_i = tile % s.nb;
-        int rest = tile / s.nb;
-        const int t1_i = rest % s.t1;
-        rest /= s.t1;
-        const int t2_i = rest % s.t2;
-        const int i3 = rest / s.t2;
-        const int i1_0 = t1_i * s.box1, i2_0 = t2_i * s.box2, n0 = nb_i * BN;
-        for (int it = 0; it < k_iters; ++it, ++it_g) {
-          const int st = it_g % stages;
-          const uint32_t ph = (it_g / stages) & 1;
-          const int tap = it / s.kc;
-          const int c0 = (it - tap * s.kc) * kBK;
-          mbar_wait(&empty_bar[st], ph ^ 1, 1);
+    // the whole warp walks the loop (warp-uniform operands); one elected lane issues the TMA
+    uint32_t it_g = 0;
+    for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x) {
+      int nb_i = tile % s.nb;
+      int rest = tile / s.nb;
+      const int t1_i = rest % s.t1;
+      rest /= s.t1;
+      const int t2_i = rest % s.t2;
+      const int i3 = rest / s.t2;
+      const int i1_0 = t1_i * s.box1, i2_0 = t2_i * s.box2, n0 = nb_i * BN;
+      int tap = 0, kc_i = 0;
+      for (int it = 0; it < k_iters; ++it, ++it_g) {
+        const int st = it_g % stages;
+        const uint32_t ph = (it_g / stages) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1, 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[st], stage_tx);
           uint8_t* sa = tiles + (size_t)st * stage_bytes;
-          tma_load_4d(sa, &p.map_a, &full_bar[st], c0, i1_0 + s.tap1[tap], i2_0 + s.tap2[tap], i3 + s.tap3[tap]);
-          tma_load_2d(sa + kABytes, &p.map_b, &full_bar[st], tap * s.c + c0, n0);
+          tma_load_4d(sa, &p.map_a, &full_bar[st], kc_i * kBK, i1_0 + s.tap1[tap], i2_0 + s.tap2[tap], i3 + s.tap3[tap]);
+          tma_load_2d(sa + kABytes, &p.map_b, &full_bar[st], tap * s.c + kc_i * kBK, n0);
+        }
+        __syncwarp();
+        if (++kc_i == s.kc) {
+          kc_i = 0;
+          ++tap;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBM, BN, 0, 0);
-      uint32_t it_g = 0;
-      uint32_t lt = 0;
-      for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aph ^ 1, 2);
+    // whole warp in the loop, one elected lane issues tcgen05.mma / commit
+    const uint32_t idesc = umma_idesc_f16(kBM, BN, 0, 0);
+    const uint32_t tiles_addr = smem_u32(tiles);
+    uint32_t it_g = 0;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aph ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256;
+      for (int it = 0; it < k_iters; ++it, ++it_g) {
+        const int st = it_g % stages;
+        const uint32_t ph = (it_g / stages) & 1;
+        mbar_wait(&full_bar[st], ph, 3);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 256;
-        for (int it = 0; it < k_iters; ++it, ++it_g) {
-          const int st = it_g % stages;
-          const uint32_t ph = (it_g / stages) & 1;
-          mbar_wait(&full_bar[st], ph, 3);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + (size_t)st * stage_bytes);
+        if (elect_one()) {
+          const uint32_t a_addr = tiles_addr + (uint32_t)st * (uint32_t)stage_bytes;
           const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
           const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes, 16, 1024);
 #pragma unroll
@@ -138,8 +146,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
             umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[st]);
+          if (it == k_iters - 1) umma_commit(&tfull_bar[as]);
         }
-        umma_commit(&tfull_bar[as]);
+        __syncwarp();
       }
     }
   } else {
@@ -160,6 +169,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       rest /= s.t1;
       const int t2_i = rest % s.t2;
       t.i3 = rest / s.t2;
+      t.t1_i = t1_i;
+      t.t2_i = t2_i;
+      t.q = q;
       const int i1 = t1_i * s.box1 + (r % s.box1);
       const int i2 = t2_i * s.box2 + (r / s.box1);
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2, epi_stage + (warp - 2) * kEpiStageBytes);
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -215,12 +227,12 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
   }
   p.b_slot_bytes = ((s.bn * kBK * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes + p.b_slot_bytes;
-  const int budget = 200 * 1024;
+  const int budget = 226 * 1024 - kEpiWarps * kEpiStageBytes - 2048;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + kEpiWarps * kEpiStageBytes + 1024;
 
   static bool attr_done = false;
   if (!attr_done) {
