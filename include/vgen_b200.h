@@ -122,6 +122,11 @@ int vgen_sinusoidal_embedding(const float* t, void* out, int64_t b, int64_t dim,
 int vgen_adaptive_avgpool(const void* x, void* y, int64_t nimg, int64_t h, int64_t w, int64_t c, int64_t oh, int64_t ow,
                           int silu_in, void* stream);
 
+/* DiagonalGaussianDistribution.sample * scale_factor (autoencoder.py:85-90,211-225): moments fp16 [n][p][2*zc]
+ * (mean | logvar, channels-last) + fp32 noise [n][zc][p] -> fp32 z [n][zc][p] */
+int vgen_vae_sample(const void* moments, const float* noise, float* z, int64_t n, int64_t zc, int64_t p, float scale,
+                    void* stream);
+
 /* ---- sampler ------------------------------------------------------------------------------------ */
 /* One fused DDIM update (diffusion_ddim.py:157-162 CFG mix, :194-196 v->x0 | :190-192 eps->x0, :230-240):
  *   out = u + g*(y-u) in fp16 (u NULL: out = y); x0; eps; xt <- c4*x0 + c5*eps (+ c6*noise).

@@ -38,7 +38,7 @@ CASES = {
     "t2v_tiny_b2": dict(kind="t2v", ctor=_T2V_TINY, seed=12, b=2, f=3, h=10, w=6, ntok=7, t=[751, 21]),
     "i2vgen_tiny": dict(kind="i2vgen", ctor=_I2V_TINY, seed=13, b=1, f=4, h=8, w=12, ntok=5, t=[961],
                         ddim=dict(steps=4, guide_scale=9.0)),
-    "vae_tiny": dict(kind="vae", ctor=_VAE_TINY, seed=14, n=2, h=8, w=12),
+    "vae_tiny": dict(kind="vae", ctor=_VAE_TINY, seed=14, n=2, h=8, w=12, encode=dict(n=2, H=32, W=48, torch_seed=77)),
 }
 
 
@@ -46,7 +46,11 @@ def make_inputs(case):
     """Deterministic inputs (numpy PCG64 keyed by tensor name, like the weights)."""
     s = case["seed"] + 1000
     if case["kind"] == "vae":
-        return {"z": synth.tensor("z", (case["n"], 4, case["h"], case["w"]), 1.0, s)}
+        d = {"z": synth.tensor("z", (case["n"], 4, case["h"], case["w"]), 1.0, s)}
+        if case.get("encode"):
+            e = case["encode"]
+            d["img"] = synth.tensor("img", (e["n"], 3, e["H"], e["W"]), 0.5, s).clamp(-1, 1)
+        return d
     b, f, h, w, L = case["b"], case["f"], case["h"], case["w"], case["ntok"]
     d = {
         "x": synth.tensor("x", (b, 4, f, h, w), 1.0, s),

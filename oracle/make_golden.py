@@ -87,6 +87,16 @@ def main():
         assert err < 2e-5, (cname, err)
         arrays = {"out": out.numpy()}
         extra = {}
+        if kind == "vae" and case.get("encode"):
+            torch.manual_seed(case["encode"]["torch_seed"])
+            zr = m.encode_firsr_stage(inp["img"], 0.18215)
+            torch.manual_seed(case["encode"]["torch_seed"])
+            zo = vo.vae_encode_first_stage(sd, inp["img"], 0.18215)
+            e3 = _maxrel(zo, zr)
+            assert e3 < 2e-5, (cname, "encode", e3)
+            arrays["encode_z"] = zr.numpy()
+            arrays["encode_moments"] = m.quant_conv(m.encoder(inp["img"])).numpy()
+            extra["encode_err"] = e3
         if case.get("ddim"):
             # full sampler on the reference: DiffusionDDIM.ddim_sample_loop with CFG
             dd = case["ddim"]

@@ -420,3 +420,31 @@ def vae_decode(sd, z):
                          u["upsample.conv.bias"], padding=1)
     h = F.silu(_gn(h, d.sub("norm_out"), 1e-6))
     return F.conv2d(h, d["conv_out.weight"], d["conv_out.bias"], padding=1)
+
+
+def vae_encode_moments(sd, x):
+    """Encoder.forward (autoencoder.py:549-578) + quant_conv (:87).  x [n,3,H,W] -> moments [n, 2*zc, H/8, W/8]."""
+    root = _SD(sd)
+    e = root.sub("encoder")
+    h = F.conv2d(x, e["conv_in.weight"], e["conv_in.bias"], padding=1)
+    levels = _children(sd, "encoder.down.")
+    for lvl in levels:
+        dn = e.sub(f"down.{lvl}")
+        for j in _children(sd, dn.p + "block."):
+            h = _vae_resnet(h, dn.sub(f"block.{j}"))
+        if dn.has("downsample.conv.weight"):
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), dn["downsample.conv.weight"], dn["downsample.conv.bias"], stride=2)
+    h = _vae_resnet(h, e.sub("mid.block_1"))
+    h = _vae_attn(h, e.sub("mid.attn_1"))
+    h = _vae_resnet(h, e.sub("mid.block_2"))
+    h = F.conv2d(F.silu(_gn(h, e.sub("norm_out"), 1e-6)), e["conv_out.weight"], e["conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def vae_encode_first_stage(sd, x, scale_factor):
+    """AutoencoderKL.encode_firsr_stage (autoencoder.py:85-90) with DiagonalGaussianDistribution.sample (:211-225):
+    the noise comes from the global CPU generator, shape of the mean."""
+    mean, logvar = torch.chunk(vae_encode_moments(sd, x), 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    noise = torch.randn(mean.shape).to(device=x.device)
+    return scale_factor * (mean + torch.exp(0.5 * logvar) * noise)

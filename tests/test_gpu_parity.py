@@ -132,3 +132,23 @@ def test_size_independent_properties_at_larger_size():
     both = m(torch.cat([xa, xb]), t2, y=y)
     sep = torch.cat([m(xa, t2[:1], y=y[:1]), m(xb, t2[1:], y=y[1:])])
     assert torch.allclose(both.float(), sep.float(), atol=2e-3, rtol=0)
+
+
+def test_vae_encode_parity(golden_dir):
+    """AutoencoderKL.encode_firsr_stage: same CPU-generator noise as the reference,
+    moments within the fp16 noise level of the fp32 truth, sample within 3e-3 relative L2."""
+    case, m, inp, sdg, gold = _setup(golden_dir, "vae_tiny")
+    img = inp["img"]
+    mom, hh, ww = m._encode_moments(img)
+    truth_m = torch.from_numpy(gold["encode_moments"]).cuda()                   # [n, 2zc, h, w]
+    mine_m = mom.view(img.shape[0], hh, ww, -1).permute(0, 3, 1, 2).float()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref16 = vo.vae_encode_moments(sdg, img)
+    e_mine, e_ref16 = _rel_l2(mine_m, truth_m), _rel_l2(ref16, truth_m)
+    print(f"vae encode moments: ours {e_mine:.3e}; reference-autocast {e_ref16:.3e}")
+    assert e_mine < 3e-3 and e_mine < 1.25 * e_ref16 + 5e-4
+    torch.manual_seed(case["encode"]["torch_seed"])
+    z = m.encode_firsr_stage(img, 0.18215)
+    truth_z = torch.from_numpy(gold["encode_z"]).cuda()
+    assert z.dtype == torch.float32 and z.shape == truth_z.shape
+    assert _rel_l2(z, truth_z) < 3e-3

@@ -185,9 +185,13 @@ print("RANK_OK", rank)
 
 
 def test_gloo_world2_broadcast_and_sharding(tmp_path):
+    import socket
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % ROOT)
+    with socket.socket() as sk:                      # a free port: back-to-back runs must not collide
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout

@@ -63,3 +63,14 @@ def test_oracle_ddim_loop_matches_reference_golden(golden_dir):
     lat = vo.ddim_sample_loop(inp["x"].clone(), lambda xt, t, **k: vo.unet_t2v_forward(sd, xt, t, **k), kw, betas,
                               case["ddim"]["guide_scale"], case["ddim"]["steps"])
     assert _maxrel(lat, torch.from_numpy(gold["ddim_latent"])) < 2e-4
+
+
+def test_oracle_vae_encode_matches_reference_golden(golden_dir):
+    torch.set_grad_enabled(False)
+    case, sd, gold = _load(golden_dir, "vae_tiny")
+    inp = make_inputs(case)
+    mom = vo.vae_encode_moments(sd, inp["img"])
+    assert _maxrel(mom, torch.from_numpy(gold["encode_moments"])) < 5e-5
+    torch.manual_seed(case["encode"]["torch_seed"])       # the reference draws the posterior noise on the CPU generator
+    z = vo.vae_encode_first_stage(sd, inp["img"], 0.18215)
+    assert _maxrel(z, torch.from_numpy(gold["encode_z"])) < 5e-5

@@ -4,8 +4,9 @@ libvgen_b200.so kernels (tcgen05 conv3x3 / 1x1, fused GroupNorm+SiLU, GEMM-based
 
 The reference runs the decoder in fp32 (outside its autocast block, inference_i2vgen_entrance.py:224-230);
 here activations are fp16 with fp32 accumulation and fp32 norm/softmax statistics, and the result is
-returned as fp32 like the reference.  `encode_firsr_stage` is a conditioning-side call (SURVEY.md
-section 8f rank 2) and is not implemented in this round: it raises instead of falling back.
+returned as fp32 like the reference.  `encode_firsr_stage` (conditioning side)
+runs the Encoder (:483-578) on the same kernels and draws the posterior noise with the CPU generator exactly
+like the reference (:223-225) so RNG streams stay aligned.
 """
 from __future__ import annotations
 
@@ -76,6 +77,20 @@ class AutoencoderKL(SpecModule):
             if lvl != 0:
                 conv3(f"decoder.up.{lvl}.upsample.conv.")
         norm("decoder.norm_out."), conv3("decoder.conv_out.")
+        # encoder (autoencoder.py:483-547)
+        conv3("encoder.conv_in.", cin_pad=8)
+        nres = len(self.plan.ch_mult)
+        for lvl in range(nres):
+            for j in range(self.plan.num_res_blocks):
+                resnet(f"encoder.down.{lvl}.block.{j}.")
+            if lvl != nres - 1:
+                conv3(f"encoder.down.{lvl}.downsample.conv.")
+        resnet("encoder.mid.block_1."), resnet("encoder.mid.block_2.")
+        a = "encoder.mid.attn_1."
+        norm(a + "norm.")
+        for nm in ("q.", "k.", "v.", "proj_out."):
+            conv1(a + nm)
+        norm("encoder.norm_out."), conv3("encoder.conv_out."), conv1("quant_conv.")
         self._packed = W
         return W
 
@@ -146,12 +161,49 @@ class AutoencoderKL(SpecModule):
         nn_, hh, ww, oc = out.shape
         return ops.pc_to_cp(out.view(nn_, hh * ww, oc), nn_, oc, hh * ww, torch.float32).view(nn_, oc, hh, ww)
 
+    @torch.no_grad()
+    def _encode_moments(self, x):
+        """Encoder.forward (autoencoder.py:549-578) + quant_conv (:87): x [n, 3, H, W] -> moments fp16 [n, hw, 2*zc]."""
+        if not x.is_cuda:
+            raise ops._l.VgenError("vgen_b200 AutoencoderKL.encode: x must be a CUDA tensor (no CPU path exists)")
+        W = self._packed or self._pack()
+        n, c, H, Wd = x.shape
+        e = "encoder."
+        h = ops.cp_to_pc(x.float().contiguous(), n, c, H * Wd, c_pad=8).view(n, H, Wd, 8)
+        h = self._conv3(h, W, e + "conv_in.")
+        nres = len(self.plan.ch_mult)
+        for lvl in range(nres):
+            for j in range(self.plan.num_res_blocks):
+                h = self._resnet(h, W, f"{e}down.{lvl}.block.{j}.")
+            if lvl != nres - 1:
+                # Downsample: F.pad (0,1,0,1) then conv 3x3 stride 2 pad 0 (autoencoder.py:462-480)
+                nn_, hh, ww, cc = h.shape
+                ho, wo = (hh + 1 - 3) // 2 + 1, (ww + 1 - 3) // 2 + 1
+                p = f"{e}down.{lvl}.downsample.conv."
+                col = ops.im2col(h, 3, 3, 2, 0, 0, ho, wo, W[p + "w"].shape[1])
+                h = ops.linear(col, W[p + "w"], bias=W[p + "b"]).view(nn_, ho, wo, W[p + "w"].shape[0])
+        h = self._resnet(h, W, e + "mid.block_1.")
+        h = self._attn(h, W, e + "mid.attn_1.")
+        h = self._resnet(h, W, e + "mid.block_2.")
+        g = ops.group_norm(h, W[e + "norm_out.g"], W[e + "norm_out.b"], 1e-6, True)
+        m = self._conv3(g, W, e + "conv_out.")                                            # [n, h, w, 2*zc]
+        nn_, hh, ww, c2 = m.shape
+        mom = ops.linear_small(m.view(-1, c2), W["quant_conv.w"], W["quant_conv.b"])
+        return mom.view(nn_, hh * ww, c2), hh, ww
+
+    @torch.no_grad()
     def encode_firsr_stage(self, x, scale_factor=1.0):
-        raise NotImplementedError("vgen_b200: AutoencoderKL.encode_firsr_stage is conditioning-side (next-round scope); "
-                                  "use the reference encoder for conditioning latents")
+        """autoencoder.py:85-90: z = scale_factor * (mean + std * randn), noise drawn on the CPU generator (:223-225)."""
+        mom, hh, ww = self._encode_moments(x)
+        n, _, c2 = mom.shape
+        zc = c2 // 2
+        noise = torch.randn(n, zc, hh, ww).to(device=x.device)
+        z = ops.vae_sample(mom, noise.view(n, zc, hh * ww).contiguous(), scale_factor)
+        return z.view(n, zc, hh, ww)
 
     def encode(self, x):
-        raise NotImplementedError("vgen_b200: AutoencoderKL.encode is out of the sampling hot path this round")
+        raise NotImplementedError("vgen_b200: AutoencoderKL.encode (returns a distribution object; training-side) is not "
+                                  "provided; use encode_firsr_stage")
 
     def forward(self, input, sample_posterior=True):
         raise NotImplementedError("vgen_b200: AutoencoderKL.forward (training) is out of scope")

@@ -62,14 +62,6 @@ static int fill_epilogue(TapGemmArgs* t, void* out, long ldo, const vgen_epilogu
   e.residual = epi ? reinterpret_cast<const __half*>(epi->residual) : nullptr;
   e.ldr = epi ? epi->residual_ld : 0;
   e.geglu = epi ? epi->geglu : 0;
-  {
-    static int staged = -1;  // VGEN_EPI_STAGED=1 selects the shared-memory transposing epilogue (A/B measurements)
-    if (staged < 0) {
-      const char* ev = getenv("VGEN_EPI_STAGED");
-      staged = (ev && ev[0] == '1') ? 1 : 0;
-    }
-    e.staged = staged;
-  }
   return 0;
 }
 

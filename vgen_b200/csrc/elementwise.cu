@@ -290,6 +290,24 @@ __global__ void ddim_step_kernel(float* __restrict__ xt, const __half* __restric
   xt[idx] = r;
 }
 
+// ------------------------------------------------------------------ VAE posterior sample
+// DiagonalGaussianDistribution.sample (autoencoder.py:211-225): moments [n][p][2*zc] fp16 channels-last
+// (mean | logvar), logvar clamped to [-30, 20], z = (mean + exp(0.5*logvar) * noise) * scale; noise and z are
+// fp32 in the reference layout [n][zc][p].
+__global__ void vae_sample_kernel(const __half* __restrict__ mom, const float* __restrict__ noise, float* __restrict__ z,
+                                  long n, int zc, long p, float scale) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * zc * p) return;
+  const long pi = idx % p;
+  const int ci = (int)((idx / p) % zc);
+  const long ni = idx / (p * zc);
+  const __half* m = mom + (ni * p + pi) * (2 * zc);
+  const float mean = __half2float(m[ci]);
+  float lv = __half2float(m[zc + ci]);
+  lv = fminf(fmaxf(lv, -30.0f), 20.0f);
+  z[idx] = (mean + expf(0.5f * lv) * noise[idx]) * scale;
+}
+
 static inline unsigned nblk(long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
 
 }  // namespace vg
@@ -414,6 +432,17 @@ int vgen_adaptive_avgpool(const void* x, void* y, int64_t nimg, int64_t h, int64
   adaptive_avgpool_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), nimg, (int)h, (int)w, (int)c, (int)oh, (int)ow, silu_in);
   VG_LAUNCH_CHECK("adaptive_avgpool_kernel");
+  return 0;
+}
+
+int vgen_vae_sample(const void* moments, const float* noise, float* z, int64_t n, int64_t zc, int64_t p, float scale,
+                    void* stream) {
+  VG_REQUIRE(moments && noise && z && n >= 0 && zc > 0 && p > 0, "vgen_vae_sample: bad arguments");
+  const long total = n * zc * p;
+  if (total == 0) return 0;
+  vae_sample_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(moments), noise, z, n, (int)zc, p, scale);
+  VG_LAUNCH_CHECK("vae_sample_kernel");
   return 0;
 }
 

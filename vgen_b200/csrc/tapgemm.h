@@ -32,7 +32,6 @@ struct TapGemmEpilogue {
   const __half* residual;    // [rows][n] or null: added after rounding
   long ldr;
   int geglu;                 // out has n/2 columns: value * gelu(gate)
-  int staged;                // 1: epilogue transposes through shared memory (coalesced stores)
 };
 
 struct TapGemmArgs {

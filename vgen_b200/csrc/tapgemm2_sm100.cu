@@ -52,7 +52,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
   uint64_t* tfull_bar = bars + 2 * stages;        // [2]       local, arrived by the multicast commit
   uint64_t* tempty_bar = bars + 2 * stages + 2;   // [2]       the leader's copy collects 8 warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars + 2 * stages + 6);  // 8 warps x kEpiStageBytes, 16B aligned
 
   const TapGemmShape& s = p.s;
   const int k_iters = s.num_taps * s.kc;
@@ -164,9 +163,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       const int rest = m / s.t1;
       const int t2_i = rest % s.t2;
       t.i3 = rest / s.t2;
-      t.t1_i = t1_i;
-      t.t2_i = t2_i;
-      t.q = q;
       const int i1 = t1_i * s.box1 + (r % s.box1);
       const int i2 = t2_i * s.box2 + (r / s.box1);
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2) && (t.i3 < s.d3);
@@ -174,7 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       mbar_wait(&tfull_bar[as], aph, 34);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2, epi_stage + (warp - 2) * kEpiStageBytes);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
@@ -218,13 +214,13 @@ int tapgemm_sm100_2cta_launch(const TapGemmArgs& a, cudaStream_t stream) {
   }
   p.b_slot_bytes = (((s.bn / 2) * kBK2 * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes2 + p.b_slot_bytes;
-  int stages = (226 * 1024 - kEpiWarps * kEpiStageBytes - 2048) / stage_bytes;
+  int stages = (224 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.m_tiles = s.d3 * s.t2 * s.t1;
   p.total_pair_tiles = ((p.m_tiles + 1) / 2) * s.nb;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + kEpiWarps * kEpiStageBytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + 1024;
 
   static bool attr_done = false;
   if (!attr_done) {

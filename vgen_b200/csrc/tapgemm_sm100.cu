@@ -60,7 +60,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
   uint64_t* tfull_bar = bars + 2 * stages;   // [2]
   uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars + 2 * stages + 6);  // 8 warps x kEpiStageBytes, 16B aligned
 
   const TapGemmShape& s = p.s;
   const int k_iters = s.num_taps * s.kc;
@@ -169,9 +168,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       rest /= s.t1;
       const int t2_i = rest % s.t2;
       t.i3 = rest / s.t2;
-      t.t1_i = t1_i;
-      t.t2_i = t2_i;
-      t.q = q;
       const int i1 = t1_i * s.box1 + (r % s.box1);
       const int i2 = t2_i * s.box2 + (r / s.box1);
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
@@ -180,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2, epi_stage + (warp - 2) * kEpiStageBytes);
+      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -227,12 +223,12 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
   }
   p.b_slot_bytes = ((s.bn * kBK * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes + p.b_slot_bytes;
-  const int budget = 226 * 1024 - kEpiWarps * kEpiStageBytes - 2048;
+  const int budget = 224 * 1024;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + kEpiWarps * kEpiStageBytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + 1024;
 
   static bool attr_done = false;
   if (!attr_done) {

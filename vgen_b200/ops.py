@@ -413,3 +413,16 @@ def ddim_step_(xt, y, u, coef7, guide_scale, mean_type_v=True, noise=None):
                                   1 if mean_type_v else 0, _stream())
     _l.check(rc, "vgen_ddim_step")
     return xt
+
+
+def vae_sample(moments, noise, scale):
+    """moments fp16 [n, p, 2*zc] (mean | logvar), noise fp32 [n, zc, p] -> fp32 z [n, zc, p]."""
+    _chk16(moments, "moments")
+    n, p, c2 = moments.shape
+    zc = c2 // 2
+    if noise.dtype != torch.float32 or not noise.is_contiguous() or noise.numel() != n * zc * p:
+        raise _l.VgenError("vae_sample: noise must be contiguous fp32 [n, zc, p]")
+    z = torch.empty(n, zc, p, device=moments.device, dtype=torch.float32)
+    rc = _l.load().vgen_vae_sample(_p(moments), _p(noise), _p(z), n, zc, p, float(scale), _stream())
+    _l.check(rc, "vgen_vae_sample")
+    return z
