@@ -1,5 +1,5 @@
 // Flash attention (head_dim 64, no mask) on tcgen05: S = Q K^T and O = P V on the 5th-gen tensor
-// cores with accumulators in TMEM, online softmax in registers (one thread per query row, so no
+// cores with BOTH accumulators in TMEM, online softmax in registers (one thread per query row, so no
 // shuffles), operands staged by TMA.
 //
 // Replaces xformers.ops.memory_efficient_attention as called by MemoryEfficientCrossAttention
@@ -10,11 +10,16 @@
 // One CTA = 256 query rows (two 128-row tiles) of one (batch, head), 10 warps:
 //   warps 0-3 / 4-7  softmax + output for q-tile 0 / 1 (thread r <-> TMEM lane r)
 //   warp 8           TMA producer: Q once, then a 2-stage ring of (K,V) blocks of 128 keys
-//   warp 9           tcgen05.mma issuer (one lane)
-// The two q-tiles ping-pong: while the softmax warps of tile 0 work on S0(j+1), the tensor core runs
-// PV1(j) and QK1(j+1).  Per key block and tile: S (128x128 fp32) lives in TMEM, P (fp16) goes through
-// shared memory in the 128B-swizzled K-major UMMA layout, P V is computed into a scratch TMEM buffer
-// and folded into a register accumulator with the usual exp(m_old - m_new) rescale.
+//   warp 9           tcgen05.mma issue (whole warp walks the loop, one elected lane issues)
+// The two q-tiles ping-pong on the tensor pipe: while the softmax warps of tile 0 work on S0(j+1), the
+// tensor core runs PV1(j) and QK1(j+1).
+//
+// Per key block and tile the softmax thread reads its 128 scores from TMEM ONCE (four tcgen05.ld in flight,
+// one wait), takes the row max, and exponentiates against a reference max m_ref that is only advanced when
+// the true max has grown by more than 2^8 ("lazy rescaling", as in FlashAttention-4): P stays <= 256, which
+// fp16 holds, so O can accumulate in TMEM across key blocks (tcgen05.mma accumulate) without a per-block
+// read-modify-write; on the rare advance the thread rescales its O row in TMEM (tcgen05.ld / st).  The final
+// O / l is exact: every term of row r carries the same 2^-m_ref factor.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -28,6 +33,7 @@ static constexpr int kQBytes = kTileQ * kD * 2;   // 16 KB
 static constexpr int kKBytes = kTileK * kD * 2;   // 16 KB
 static constexpr int kPBytes = kTileQ * kTileK * 2;  // 32 KB per q-tile
 static constexpr int kKvStages = 2;
+static constexpr float kRescaleThreshold = 8.0f;     // log2 units: P <= 2^8
 
 struct alignas(64) AttnParams {
   CUtensorMap map_q;  // {64, H, Lq, B}
@@ -51,10 +57,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
   uint64_t* q_full = bars;            // [1]
   uint64_t* kv_full = bars + 1;       // [2]
   uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // [2] per q-tile
-  uint64_t* p_full = bars + 7;        // [2]
-  uint64_t* o_full = bars + 9;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* s_full = bars + 5;        // [2] per q-tile: S(j) written by QK
+  uint64_t* p_full = bars + 7;        // [2] per q-tile: P(j) in smem, S(j) consumed, O rescaled
+  uint64_t* o_full = bars + 9;        // [2] per q-tile: PV(j) finished (P buffer free, O readable)
+  uint64_t* s_free = bars + 11;       // [2] per q-tile: S(j) is in registers, QK(j+1) may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
@@ -72,6 +79,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     fence_mbar_init();
   }
@@ -86,60 +94,89 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
   // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
   if (warp == 8) {
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    const int kvb = batch / p.kv_batch_div;
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * kQBytes);
       tma_load_4d(sQ, &p.map_q, q_full, 0, head, q0, batch);
       tma_load_4d(sQ + kQBytes, &p.map_q, q_full, 0, head, q0 + kTileQ, batch);
-      const int kvb = batch / p.kv_batch_div;
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j % kKvStages;
-        const uint32_t ph = (j / kKvStages) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1, 10);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j % kKvStages;
+      const uint32_t ph = (j / kKvStages) & 1;
+      mbar_wait(&kv_empty[st], ph ^ 1, 10);
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[st], 2 * kKBytes);
         uint8_t* dst = sKV + st * 2 * kKBytes;
         tma_load_4d(dst, &p.map_k, &kv_full[st], 0, head, j * kTileK, kvb);
         tma_load_4d(dst + kKBytes, &p.map_v, &kv_full[st], 0, head, j * kTileK, kvb);
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      const uint32_t idesc_qk = umma_idesc_f16(kTileQ, kTileK, 0, 0);
-      const uint32_t idesc_pv = umma_idesc_f16(kTileQ, kD, 0, 1);  // B (= V) is MN-major
-      auto issue_qk = [&](int i, int j) {
-        const int st = j % kKvStages;
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(sQ + i * kQBytes), 16, 1024);
-        const uint64_t b_desc = umma_desc_sw128(smem_u32(sKV + st * 2 * kKBytes), 16, 1024);
+    // ------------------------------------------------------------------ MMA issue (warp-uniform loop)
+    const uint32_t idesc_qk = umma_idesc_f16(kTileQ, kTileK, 0, 0);
+    const uint32_t idesc_pv = umma_idesc_f16(kTileQ, kD, 0, 1);  // B (= V) is MN-major
+    const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV), p_addr0 = smem_u32(sP);
+    auto issue_qk = [&](int i, int j) {
+      if (elect_one()) {
+        const uint64_t a_desc = umma_desc_sw128(q_addr + i * kQBytes, 16, 1024);
+        const uint64_t b_desc = umma_desc_sw128(kv_addr + (j % kKvStages) * 2 * kKBytes, 16, 1024);
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) umma_f16_ss(tmem + i * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[i]);
-      };
-      mbar_wait(q_full, 0, 11);
-      mbar_wait(&kv_full[0], 0, 12);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      for (int j = 0; j < nkv; ++j) {
+      }
+      __syncwarp();
+    };
+    // Event-driven issue: QK_i(j+1) goes out as soon as the softmax warps of tile i have pulled S_i(j) into
+    // registers (s_free), i.e. it overlaps their exponentials; PV_i(j) goes out when P_i(j) is in shared memory.
+    auto issue_pv = [&](int i, int j, bool release_kv) {
+      if (elect_one()) {
         const int st = j % kKvStages;
-        if (j + 1 < nkv) {
-          mbar_wait(&kv_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1, 13);
-        }
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], j & 1, 14);
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(sKV + st * 2 * kKBytes + kKBytes);
-          const uint32_t p_addr = smem_u32(sP + i * kPBytes);
+        const uint32_t v_addr = kv_addr + st * 2 * kKBytes + kKBytes;
+        const uint32_t p_addr = p_addr0 + i * kPBytes;
 #pragma unroll
-          for (int ks = 0; ks < kTileK / 16; ++ks) {
-            // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
-            const uint64_t a_desc = umma_desc_sw128(p_addr + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 16, 1024);
-            // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart
-            const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
-            umma_f16_ss(tmem + 256 + i * 64, a_desc, b_desc, idesc_pv, ks != 0);
-          }
-          umma_commit(&o_full[i]);
-          if (i == 1) umma_commit(&kv_empty[st]);  // K(j), V(j) fully consumed by both tiles
-          if (j + 1 < nkv) issue_qk(i, j + 1);
+        for (int ks = 0; ks < kTileK / 16; ++ks) {
+          // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
+          const uint64_t a_desc = umma_desc_sw128(p_addr + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 16, 1024);
+          // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart
+          const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
+          umma_f16_ss(tmem + 256 + i * 64, a_desc, b_desc, idesc_pv, (j | ks) != 0);  // O accumulates over blocks
         }
+        umma_commit(&o_full[i]);
+        if (release_kv) umma_commit(&kv_empty[st]);  // K(j), V(j) fully consumed by both tiles
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0, 11);
+    int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
+    long long t_idle = 0;
+    while (pv_next[0] < nkv || pv_next[1] < nkv) {
+      bool progressed = false;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int jq = qk_next[i];
+        if (jq < nkv && (jq == 0 || mbar_test_wait(&s_free[i], (jq - 1) & 1)) &&
+            mbar_test_wait(&kv_full[jq % kKvStages], (jq / kKvStages) & 1)) {
+          tc_fence_after();
+          issue_qk(i, jq);
+          qk_next[i] = jq + 1;
+          progressed = true;
+        }
+        const int jp = pv_next[i];
+        if (jp < nkv && mbar_test_wait(&p_full[i], jp & 1)) {
+          tc_fence_after();
+          issue_pv(i, jp, pv_next[1 - i] > jp);
+          pv_next[i] = jp + 1;
+          progressed = true;
+        }
+      }
+      if (progressed) {
+        t_idle = 0;
+      } else {
+        if (t_idle == 0) t_idle = clock64();
+        else if (clock64() - t_idle > VG_WATCHDOG_CYCLES) mbar_deadlock(15, 0);
       }
     }
   } else {
@@ -150,112 +187,138 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t t_s = tmem + i * 128 + lane_base;
     const uint32_t t_o = tmem + 256 + i * 64 + lane_base;
-    uint8_t* prow = sP + i * kPBytes + r * 128;
+    const uint32_t prow = smem_u32(sP + i * kPBytes + r * 128);
     const int sw = r & 7;
+    const float sl2 = p.scale_log2;
 
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-    float o_acc[kD];
-#pragma unroll
-    for (int d = 0; d < kD; ++d) o_acc[d] = 0.f;
+    float m_ref = -INFINITY;  // reference max (raw score units) all of this row's exponentials are relative to
+    float l_run = 0.f;
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full[i], j & 1, 20);
       tc_fence_after();
       const int valid = p.lk - j * kTileK;  // keys valid in this block (>= 128 unless last)
-      // pass 1: row max
-      float m_blk = -INFINITY;
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld32(t_s + 0, s0);
+      tmem_ld32(t_s + 32, s1);
+      tmem_ld32(t_s + 64, s2);
+      tmem_ld32(t_s + 96, s3);
+      tmem_ld_wait();
+      if (valid < kTileK) {  // last, partial block: masked keys must not contribute
 #pragma unroll
-      for (int c = 0; c < kTileK; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c, v);
-        tmem_ld_wait();
-        if (valid >= c + 32) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) m_blk = fmaxf(m_blk, __uint_as_float(v[t]));
-        } else {
-#pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (c + t < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[t]));
+        for (int t = 0; t < 32; ++t) {
+          if (t >= valid) s0[t] = 0xff800000u;
+          if (32 + t >= valid) s1[t] = 0xff800000u;
+          if (64 + t >= valid) s2[t] = 0xff800000u;
+          if (96 + t >= valid) s3[t] = 0xff800000u;
         }
       }
-      const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = fast_exp2((m_run - m_new) * p.scale_log2);  // 0 on the first block (m_run = -inf)
-      const float neg_ms = -m_new * p.scale_log2;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[t]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[t]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[t]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[t]));
+      }
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
-      // fold the previous block's P V into the accumulator (also guarantees P(j-1) has been consumed)
+      // P(j-1) consumed and O(j-1) complete before P(j) is written / O is touched
       if (j > 0) {
         mbar_wait(&o_full[i], (j - 1) & 1, 21);
         tc_fence_after();
+      }
+      // advance the reference max only when the true max has outgrown it by more than the threshold
+      const bool grow = (m_blk - m_ref) * sl2 > kRescaleThreshold;   // always true on the first block
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? m_blk : m_ref;
+        const float alpha = (j == 0) ? 0.f : fast_exp2((m_ref - m_new) * sl2);  // 1 for rows that do not advance
+        if (j > 0) {
+          // rescale this row of O in TMEM; the score registers are dead here and reloaded afterwards
+          uint32_t o[32];
+#pragma unroll 1
+          for (int c = 0; c < kD; c += 32) {
+            tmem_ld32(t_o + c, o);
+            tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < kD; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_o + c, v);
+            for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+            tmem_st32(t_o + c, o);
+          }
+          tmem_st_wait();
+          tmem_ld32(t_s + 0, s0);
+          tmem_ld32(t_s + 32, s1);
+          tmem_ld32(t_s + 64, s2);
+          tmem_ld32(t_s + 96, s3);
           tmem_ld_wait();
+          if (valid < kTileK) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) o_acc[c + t] = o_acc[c + t] * alpha_prev + __uint_as_float(v[t]);
+            for (int t = 0; t < 32; ++t) {
+              if (t >= valid) s0[t] = 0xff800000u;
+              if (32 + t >= valid) s1[t] = 0xff800000u;
+              if (64 + t >= valid) s2[t] = 0xff800000u;
+              if (96 + t >= valid) s3[t] = 0xff800000u;
+            }
+          }
         }
+        l_run *= alpha;
+        m_ref = m_new;
       }
-      // pass 2: p = exp2(s*scale*log2e - m*scale*log2e), row sum, P -> smem (swizzled K-major)
-      float l_blk = 0.f;
-#pragma unroll
-      for (int c = 0; c < kTileK; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c, v);
-        tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float e = fast_exp2(fmaf(__uint_as_float(v[t]), p.scale_log2, neg_ms));
-          if (c + t >= valid) e = 0.f;
-          pv[t] = e;
-          l_blk += e;
-        }
-        uint8_t* chunk = prow + (c >> 6) * (kTileQ * 128);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_half2(pv[g * 8 + 0], pv[g * 8 + 1]);
-          u.y = pack_half2(pv[g * 8 + 2], pv[g * 8 + 3]);
-          u.z = pack_half2(pv[g * 8 + 4], pv[g * 8 + 5]);
-          u.w = pack_half2(pv[g * 8 + 6], pv[g * 8 + 7]);
-          const int piece = ((c & 63) >> 3) + g;  // 16-byte piece index inside the 128 B row
-          *reinterpret_cast<uint4*>(chunk + ((piece ^ sw) << 4)) = u;
-        }
-      }
-      l_run = l_run * alpha + l_blk;
-      m_run = m_new;
-      alpha_prev = alpha;
-      // S(j) fully read and P(j) written: publish to the MMA warp
+      // the scores are in registers for good: let the tensor core start QK(j+1) into this S buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[i]);
+      const float neg_ms = -m_ref * sl2;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      // p = exp2(s*scale*log2e - m_ref*scale*log2e), row sum, P -> smem (128B-swizzled K-major UMMA layout)
+#define VG_ATTN_EMIT(ARR, C0, LSUM)                                                          \
+  {                                                                                          \
+    const uint32_t chunk = prow + ((C0) >> 6) * (kTileQ * 128);                              \
+    _Pragma("unroll") for (int g = 0; g < 4; ++g) {                                          \
+      float e[8];                                                                            \
+      _Pragma("unroll") for (int t = 0; t < 8; ++t) {                                        \
+        e[t] = fast_exp2(fmaf(__uint_as_float(ARR[g * 8 + t]), sl2, neg_ms));                \
+        LSUM += e[t];                                                                        \
+      }                                                                                      \
+      const int piece = (((C0) & 63) >> 3) + g; /* 16-byte piece inside the 128 B row */     \
+      st_shared_v4(chunk + ((piece ^ sw) << 4), pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), \
+                   pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));                          \
+    }                                                                                        \
+  }
+      VG_ATTN_EMIT(s0, 0, l0)
+      VG_ATTN_EMIT(s1, 32, l1)
+      VG_ATTN_EMIT(s2, 64, l2)
+      VG_ATTN_EMIT(s3, 96, l3)
+#undef VG_ATTN_EMIT
+      l_run += (l0 + l1) + (l2 + l3);
+      // S(j) consumed, P(j) written, O rescaled: publish to the MMA warp
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[i]);
     }
-    // last block's P V
+    // ---- output: O / l
     mbar_wait(&o_full[i], (nkv - 1) & 1, 22);
     tc_fence_after();
     const int row = q0 + i * kTileQ + r;
     const float inv_l = 1.0f / l_run;
     __half* orow = p.out + (long)batch * p.out_batch_stride + (long)row * p.ldo + head * kD;
-#pragma unroll
-    for (int c = 0; c < kD; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(t_o + c, v);
-      tmem_ld_wait();
-      if (row < p.lq) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) f[t] = (o_acc[c + g * 8 + t] * alpha_prev + __uint_as_float(v[g * 8 + t])) * inv_l;
-          uint4 u;
-          u.x = pack_half2(f[0], f[1]);
-          u.y = pack_half2(f[2], f[3]);
-          u.z = pack_half2(f[4], f[5]);
-          u.w = pack_half2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
-        }
-      }
+    uint32_t oa[32], ob[32];
+    tmem_ld32(t_o + 0, oa);
+    tmem_ld32(t_o + 32, ob);
+    tmem_ld_wait();
+    if (row < p.lq) {
+#define VG_ATTN_STORE(ARR, C0)                                                                                  \
+  _Pragma("unroll") for (int g = 0; g < 4; ++g) {                                                               \
+    uint4 u;                                                                                                    \
+    u.x = pack_half2(__uint_as_float(ARR[g * 8 + 0]) * inv_l, __uint_as_float(ARR[g * 8 + 1]) * inv_l);         \
+    u.y = pack_half2(__uint_as_float(ARR[g * 8 + 2]) * inv_l, __uint_as_float(ARR[g * 8 + 3]) * inv_l);         \
+    u.z = pack_half2(__uint_as_float(ARR[g * 8 + 4]) * inv_l, __uint_as_float(ARR[g * 8 + 5]) * inv_l);         \
+    u.w = pack_half2(__uint_as_float(ARR[g * 8 + 6]) * inv_l, __uint_as_float(ARR[g * 8 + 7]) * inv_l);         \
+    *reinterpret_cast<uint4*>(orow + (C0) + g * 8) = u;                                                         \
+  }
+      VG_ATTN_STORE(oa, 0)
+      VG_ATTN_STORE(ob, 32)
+#undef VG_ATTN_STORE
     }
   }
 
@@ -313,7 +376,7 @@ extern "C" int vgen_attention_d64(const void* q, const void* k, const void* v, v
   p.heads = (int)heads;
   p.kv_batch_div = (int)kv_batch_div;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 2 * kPBytes + 12 * 8 + 16 + 1024;
+  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 2 * kPBytes + 14 * 8 + 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
