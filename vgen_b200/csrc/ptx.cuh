@@ -241,6 +241,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrivals that only hand a TMEM buffer back (ordering is provided by tcgen05.wait::ld + tcgen05.fence): no
+// memory release is needed, and the default .release form costs a MEMBAR that waits for the epilogue's
+// outstanding global stores (7-10 % of the short-K kernels' samples).
+__device__ __forceinline__ void mbar_arrive_relaxed_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // TMA loads whose completion is signalled on an mbarrier that may live in the PEER CTA (the leader's)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
                                                 int c1) {

@@ -167,13 +167,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       const int i2 = t2_i * s.box2 + (r / s.box1);
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2) && (t.i3 < s.d3);
       t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
+      if (e.residual && t.row_ok && !e.geglu) {
+        // the residual row segment comes from HBM: start pulling it into L2 while the tile's MMAs are still running
+        const __half* rp = e.residual + t.row * e.ldr + t.nb_i * BN;
+        for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN && t.nb_i * BN + c0 < s.n; c0 += 64)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c0));
+      }
       mbar_wait(&tfull_bar[as], aph, 34);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
       tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (lane == 0) mbar_arrive_relaxed_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
     }
   }
 

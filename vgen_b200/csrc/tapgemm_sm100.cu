@@ -173,6 +173,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
       t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
 
+      if (e.residual && t.row_ok && !e.geglu) {
+        // the residual row segment comes from HBM: start pulling it into L2 while the tile's MMAs are still running
+        const __half* rp = e.residual + t.row * e.ldr + t.nb_i * BN;
+        for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN && t.nb_i * BN + c0 < s.n; c0 += 64)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c0));
+      }
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive_relaxed(&tempty_bar[as]);
     }
   }
 

@@ -226,7 +226,8 @@ def group_norm(x, gamma, beta, eps, silu, n=None, out=None):
     ws = _gn_workspace(x.device, n)
     rc = _run("group_norm", 0.0, 4.0 * x.numel(),
               lambda: _l.load().vgen_group_norm(_p(x), _p(out), n, p, c, _p(gamma), _p(beta), float(eps), 1 if silu else 0,
-                                                _p(ws), _stream()))
+                                                _p(ws), _stream()),
+              tag=f"n{n} p{p} c{c}")
     _l.check(rc, "vgen_group_norm")
     return out
 
@@ -239,7 +240,8 @@ def layer_norm(x, gamma, beta, eps=1e-5, out=None):
         out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
     rc = _run("layer_norm", 0.0, 4.0 * rows * c,
-              lambda: _l.load().vgen_layer_norm(_p(x2), _p(o2), rows, c, ldx, ldo, _p(gamma), _p(beta), float(eps), _stream()))
+              lambda: _l.load().vgen_layer_norm(_p(x2), _p(o2), rows, c, ldx, ldo, _p(gamma), _p(beta), float(eps), _stream()),
+              tag=f"rows{rows} c{c}")
     _l.check(rc, "vgen_layer_norm")
     return out
 
