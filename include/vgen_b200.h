@@ -127,6 +127,28 @@ int vgen_adaptive_avgpool(const void* x, void* y, int64_t nimg, int64_t h, int64
 int vgen_vae_sample(const void* moments, const float* noise, float* z, int64_t n, int64_t zc, int64_t p, float scale,
                     void* stream);
 
+/* ---- model-variant prologues (variants.cu) -------------------------- */
+/* softmax(q k^T * scale) v for any head_dim <= 256 and ragged (lq, lk); same addressing as
+ * vgen_attention_d64.  Serves the 16-token context transformer of UNetSD_HiGen (head_dim 160).
+ * replaces: CrossAttention / memory_efficient_attention inside TextContextCrossTransformerMultiLayer,
+ * unet_higen.py:154-172 (BasicTransformerBlock util.py:674-741) */
+int vgen_attention_cross_small(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
+                               int64_t lq, int64_t lk, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv,
+                               int64_t ldo, int64_t kv_batch_div, float scale, void* stream);
+/* F.interpolate(x.transpose(1,2), size=lout, mode='linear').transpose(1,2) on x[nseq][lin][c] fp16
+ * (motion embedding, unet_higen.py:389-392) */
+int vgen_interp_linear_rows(const void* x, void* y, int64_t nseq, int64_t lin, int64_t lout, int64_t c, void* stream);
+/* Fourier_filter(x, threshold=1, scale) of unet_sr600.py:30-49 on channels-last x[nimg][h][w][ldx] (first c
+ * channels), written to y[nimg][h][w][ldy]: the four centre bins of the shifted spectrum are scaled. */
+int vgen_fourier_lowfreq_filter(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t nimg, int64_t h, int64_t w,
+                                int64_t c, float scale, void* stream);
+/* UpsampleSR600 (util.py:792-804): nearest x2, keeping output rows [row0, row0+rows_out) of the 2h rows */
+int vgen_upsample_nearest2x_rows(const void* x, void* y, int64_t nimg, int64_t h, int64_t w, int64_t c, int64_t row0,
+                                 int64_t rows_out, void* stream);
+/* dst[r][0:cols] = fp16(src[r][0:cols] * s) with row strides ("x[:, :C/2] *= 1.1", unet_sr600.py:272-273,279) */
+int vgen_scale_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, float s,
+                      void* stream);
+
 /* ---- sampler ------------------------------------------------------------------------------------ */
 /* One fused DDIM update (diffusion_ddim.py:157-162 CFG mix, :194-196 v->x0 | :190-192 eps->x0, :230-240):
  *   out = u + g*(y-u) in fp16 (u NULL: out = y); x0; eps; xt <- c4*x0 + c5*eps (+ c6*noise).

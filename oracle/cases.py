@@ -18,6 +18,9 @@ _I2V_TINY = dict(_T2V_TINY, concat_dim=4)
 _VAE_TINY = dict(ddconfig=dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=32,
                                ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[], dropout=0.0), embed_dim=4)
 
+_LCM_TINY = dict(_T2V_TINY, concat_dim=8, num_tokens=4)       # + config.video_compositions == ['text']
+_HIGEN_TINY = dict(_T2V_TINY, context_embedding_depth=1, num_tokens=3)
+
 # the effective constructor kwargs of the BASELINE configs
 _FULL_UNET = dict(in_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
                   head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], dropout=0.1, temporal_attention=True,
@@ -29,7 +32,13 @@ FULL_CTORS = {
     "full_t2v": ("t2v", _FULL_UNET),
     "full_i2vgen": ("i2vgen", dict(_FULL_UNET, concat_dim=4)),
     "full_vae": ("vae", _FULL_VAE),
+    # configs/videolcm_t2v_infer.yaml:46-66, sr600_infer.yaml:21-40, higen_infer.yaml (UNet section)
+    "full_videolcm": ("videolcm", dict(_FULL_UNET, concat_dim=8, num_tokens=4)),
+    "full_sr600": ("sr600", dict(_FULL_UNET)),
+    "full_higen": ("higen", dict(_FULL_UNET, context_embedding_depth=2, num_tokens=16)),
 }
+
+LCM_CONFIG = dict(video_compositions=["text"], resolution=[448, 256])  # the `config` object UNetSD_VideoLCM reads (unet_videolcm.py:262-270)
 
 CASES = {
     # name: kind, ctor kwargs, weight seed, input shape recipe
@@ -38,6 +47,10 @@ CASES = {
     "t2v_tiny_b2": dict(kind="t2v", ctor=_T2V_TINY, seed=12, b=2, f=3, h=10, w=6, ntok=7, t=[751, 21]),
     "i2vgen_tiny": dict(kind="i2vgen", ctor=_I2V_TINY, seed=13, b=1, f=4, h=8, w=12, ntok=5, t=[961],
                         ddim=dict(steps=4, guide_scale=9.0)),
+    "videolcm_tiny": dict(kind="videolcm", ctor=_LCM_TINY, seed=15, b=1, f=4, h=8, w=12, ntok=5, t=[259]),
+    "sr600_tiny": dict(kind="sr600", ctor=_T2V_TINY, seed=16, b=1, f=3, h=10, w=12, ntok=6, t=[600]),
+    "higen_tiny": dict(kind="higen", ctor=_HIGEN_TINY, seed=17, b=2, f=3, h=8, w=6, ntok=5, t=[801, 333]),
+    "higen_tiny_f1": dict(kind="higen", ctor=_HIGEN_TINY, seed=17, b=2, f=1, h=8, w=6, ntok=5, t=[401, 99]),
     "vae_tiny": dict(kind="vae", ctor=_VAE_TINY, seed=14, n=2, h=8, w=12, encode=dict(n=2, H=32, W=48, torch_seed=77)),
 }
 
@@ -63,4 +76,11 @@ def make_inputs(case):
         li = synth.tensor("local_image", (b, 4, 1, h, w), 0.18215, s)
         d["local_image"] = li.repeat(1, 1, f, 1, 1)
         d["fps"] = torch.tensor([16] * b, dtype=torch.long)
+    if case["kind"] == "higen":
+        d["spat_prior"] = synth.tensor("spat_prior", (b, 4, h, w), 0.5, s)
+        if f > 1:   # stage 2 (inference_higen_entrance.py:221-229): one motion factor per frame transition
+            d["motion_cond"] = torch.tensor([[300 + 50 * i + 7 * j for j in range(f - 1)] for i in range(b)], dtype=torch.long)
+        else:       # stage 1 (:198-203)
+            d["motion_cond"] = torch.tensor([0] * b, dtype=torch.long)
+        d["appearance_cond"] = synth.tensor("appearance_cond", (b, f, 32), 0.5, s).abs().clamp(0, 1)
     return d

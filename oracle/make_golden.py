@@ -22,13 +22,25 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from oracle import refload, synth, vgen_oracle as vo  # noqa: E402
-from oracle.cases import CASES, make_inputs  # noqa: E402
+from oracle.cases import CASES, LCM_CONFIG, make_inputs  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
 def _maxrel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def build_variant(ref, kind, ctor):
+    """The a21 model variants: constructor calls as the inference entrances make them."""
+    if kind == "videolcm":
+        from easydict import EasyDict
+        return ref.UNetSD_VideoLCM(config=EasyDict(**LCM_CONFIG), **ctor)
+    if kind == "sr600":
+        return ref.UNetSD_SR600(**ctor)
+    if kind == "higen":
+        return ref.UNetSD_HiGen(**ctor)
+    raise ValueError(kind)
 
 
 def main():
@@ -69,7 +81,7 @@ def main():
         elif kind == "vae":
             m = ref.AutoencoderKL(**case["ctor"]).eval()
         else:
-            raise ValueError(kind)
+            m = build_variant(ref, kind, case["ctor"]).eval()
         spec = synth.spec_of(m)
         sd = synth.state_dict(spec, seed=case["seed"])
         m.load_state_dict(sd, strict=True)
@@ -80,6 +92,16 @@ def main():
         elif kind == "i2vgen":
             out = m(inp["x"], inp["t"], y=inp["y"], image=inp["image"], local_image=inp["local_image"], fps=inp["fps"])
             mine = vo.unet_i2vgen_forward(sd, inp["x"], inp["t"], inp["y"], inp["image"], inp["local_image"], inp["fps"])
+        elif kind == "videolcm":
+            out = m(inp["x"], inp["t"], y=inp["y"])
+            mine = vo.unet_videolcm_forward(sd, inp["x"], inp["t"], inp["y"])
+        elif kind == "sr600":
+            out = m(inp["x"], inp["t"], inp["y"])
+            mine = vo.unet_sr600_forward(sd, inp["x"], inp["t"], inp["y"])
+        elif kind == "higen":
+            hk = dict(spat_prior=inp["spat_prior"], motion_cond=inp["motion_cond"], appearance_cond=inp["appearance_cond"])
+            out = m(inp["x"], inp["t"], y=inp["y"], **hk)
+            mine = vo.unet_higen_forward(sd, inp["x"], inp["t"], inp["y"], **hk)
         else:
             out = m.decode(inp["z"])
             mine = vo.vae_decode(sd, inp["z"])
@@ -128,7 +150,10 @@ def main():
     from oracle.cases import FULL_CTORS
     for name, (kind, ctor) in FULL_CTORS.items():
         with torch.device("meta"):
-            m = {"t2v": ref.UNetSD_T2VBase, "i2vgen": ref.UNetSD_I2VGen, "vae": ref.AutoencoderKL}[kind](**ctor)
+            if kind in ("t2v", "i2vgen", "vae"):
+                m = {"t2v": ref.UNetSD_T2VBase, "i2vgen": ref.UNetSD_I2VGen, "vae": ref.AutoencoderKL}[kind](**ctor)
+            else:
+                m = build_variant(ref, kind, ctor)
         spec = synth.spec_of(m)
         with open(os.path.join(GOLD, f"{name}.spec.json"), "w") as fh:
             json.dump([[k, list(s)] for k, s in spec], fh)

@@ -9,6 +9,9 @@ that is not installed; the stubs below provide the same arithmetic on CPU:
     reference call sites tools/modules/unet/util.py:254,259)
   * fairscale checkpoint_wrapper            -> identity (it is a no-op under no_grad)
   * Tensor.cuda                             -> identity (unet_i2vgen.py:283 hard-codes .cuda())
+  * torchsde.BrownianTree                   -> oracle/brownian.py (a seeded Brownian-bridge tree with the same
+    call interface; torchsde is a pip dependency of the reference, absent here and on the GPU box, so
+    the stochastic term of sample_dpmpp_2m_sde is pinned on the SAME stub for both sides)
 and fake parent packages keep tools/__init__.py (which imports every engine) from running.
 """
 from __future__ import annotations
@@ -52,6 +55,9 @@ def _install_stubs():
         _stub("fairscale")
         _stub("fairscale.nn")
         _stub("fairscale.nn.checkpoint", checkpoint_wrapper=lambda m, *a, **k: m)
+    if "torchsde" not in sys.modules:
+        from . import brownian
+        _stub("torchsde", BrownianTree=brownian.BrownianTree)
     if "easydict" not in sys.modules:
         class EasyDict(dict):
             def __getattr__(self, k):
@@ -89,6 +95,12 @@ def load():
     ae = importlib.import_module("tools.modules.autoencoder")
     util = importlib.import_module("tools.modules.unet.util")
     reg = importlib.import_module("utils.registry_class")
+    lcm = importlib.import_module("tools.modules.unet.unet_videolcm")
+    sr = importlib.import_module("tools.modules.unet.unet_sr600")
+    hig = importlib.import_module("tools.modules.unet.unet_higen")
+    gauss = importlib.import_module("tools.modules.diffusions.diffusion_gauss")
+    _loaded.update(UNetSD_VideoLCM=lcm.UNetSD_VideoLCM, UNetSD_SR600=sr.UNetSD_SR600, UNetSD_HiGen=hig.UNetSD_HiGen,
+                   diffusion_gauss=gauss, diffusion_ddim=ddim)
     _loaded.update(UNetSD_T2VBase=t2v.UNetSD_T2VBase, UNetSD_I2VGen=i2v.UNetSD_I2VGen,
                    DiffusionDDIM=ddim.DiffusionDDIM, schedules=sched, AutoencoderKL=ae.AutoencoderKL,
                    util=util, registry=reg)

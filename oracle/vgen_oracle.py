@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- the oracle for the VGen sampling hot path.
 
 A plain-PyTorch (fp32 by default) restatement of what the reference computes on the path
-    DiffusionDDIM.ddim_sample_loop -> UNetSD_T2VBase / UNetSD_I2VGen forward -> AutoencoderKL.decode,
+    DiffusionDDIM.ddim_sample_loop -> UNetSD_T2VBase / UNetSD_I2VGen (+ VideoLCM / SR600 / HiGen variants)
+    forward -> AutoencoderKL.decode,
 written from the reference's arithmetic, not from its module tree: every function works directly on a
 reference-format state_dict (dict name -> tensor) and derives the block structure from the key names.
 Each function cites the reference lines it follows (paths relative to the reference root).
@@ -191,18 +192,21 @@ def _basic_block(x, ctx, s, heads):
     return x
 
 
-def _temporal_conv(x5, s):
+def _temporal_conv(x5, s, woimg=False):
     """TemporalConvBlock_v2.forward, util.py:1686-1697.  x5: [b, c, f, h, w]; GroupNorm statistics
-    span all frames; conv is (3,1,1) with zero padding over f."""
+    span all frames; conv is (3,1,1) with zero padding over f.  woimg: TemporalConvBlock_v2WoImg
+    (unet_higen.py:71-85) multiplies the branch by 0.0 when there is a single frame."""
     h = x5
     for name, widx in (("conv1", 2), ("conv2", 3), ("conv3", 3), ("conv4", 3)):
         c = s.sub(name)
         h = F.silu(F.group_norm(h, 32, c["0.weight"], c["0.bias"], 1e-5))
         h = F.conv3d(h, c[f"{widx}.weight"], c[f"{widx}.bias"], padding=(1, 0, 0))
+    if woimg and x5.size(2) == 1:
+        return x5 + 0.0 * h
     return x5 + h
 
 
-def _res_block(x, emb, s, batch):
+def _res_block(x, emb, s, batch, woimg=False):
     """ResBlock._forward, util.py:900-927 (use_scale_shift_norm False, no up/down).  x: [(b f), c, h, w]."""
     h = F.conv2d(F.silu(_gn(x, s.sub("in_layers.0"), 1e-5)), s["in_layers.2.weight"], s["in_layers.2.bias"], padding=1)
     e = _lin(F.silu(emb), s.sub("emb_layers.1")).type(h.dtype)
@@ -212,7 +216,7 @@ def _res_block(x, emb, s, batch):
     h = skip + h
     bf, c, hh, ww = h.shape
     h5 = h.reshape(batch, bf // batch, c, hh, ww).permute(0, 2, 1, 3, 4)
-    h5 = _temporal_conv(h5, s.sub("temopral_conv"))  # (sic) the typo is part of the checkpoint format
+    h5 = _temporal_conv(h5, s.sub("temopral_conv"), woimg)  # (sic) the typo is part of the checkpoint format
     return h5.permute(0, 2, 1, 3, 4).reshape(bf, c, hh, ww)
 
 
@@ -226,7 +230,7 @@ def _spatial_transformer(x, ctx, s, head_dim):
     return h.reshape(bf, hh, ww, c).permute(0, 3, 1, 2) + x
 
 
-def _temporal_transformer(x, s, head_dim, batch):
+def _temporal_transformer(x, s, head_dim, batch, woimg=False):
     """TemporalTransformer.forward (use_linear=False, only_self_att=True), util.py:1240-1286.
     x: [(b f), c, h, w]; tokens are the f frames of one pixel; both attentions are self-attention."""
     bf, c, hh, ww = x.shape
@@ -238,22 +242,28 @@ def _temporal_transformer(x, s, head_dim, batch):
     h = _basic_block(h, None, s.sub("transformer_blocks.0"), h.shape[-1] // head_dim)
     h = F.linear(h, s["proj_out.weight"][:, :, 0], s["proj_out.bias"])
     h = h.reshape(batch, hh, ww, f, c).permute(0, 3, 4, 1, 2).reshape(bf, c, hh, ww)
+    if woimg and f == 1:                                                 # TemporalTransformerWoImg, unet_higen.py:146-149
+        return 0.0 * h + x
     return h + x
 
 
-def _run_block(x, s, emb, ctx, head_dim, batch):
+def _run_block(x, s, emb, ctx, head_dim, batch, woimg=False, sr600=False):
     """One entry of input_blocks / middle_block / output_blocks: dispatch on the parameters present
     (the reference dispatches on module type, unet_t2v.py:280-348)."""
     if s.has("in_layers.0.weight"):
-        return _res_block(x, emb, s, batch)
+        return _res_block(x, emb, s, batch, woimg)
     if s.has("transformer_blocks.0.norm1.weight"):
         if s["proj_in.weight"].ndim == 2:
             return _spatial_transformer(x, ctx, s, head_dim)
-        return _temporal_transformer(x, s, head_dim, batch)
+        return _temporal_transformer(x, s, head_dim, batch, woimg)
     if s.has("op.weight"):                                    # Downsample: conv3x3 stride 2, util.py:946
-        return F.conv2d(x, s["op.weight"], s["op.bias"], stride=2, padding=1)
+        # UNetSD_SR600 pads the height by 2 (unet_sr600.py:151-153) so that odd heights survive the round trip
+        return F.conv2d(x, s["op.weight"], s["op.bias"], stride=2, padding=(2, 1) if sr600 else 1)
     if s.has("conv.weight"):                                  # Upsample: nearest x2 then conv, util.py:761-771
-        return F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), s["conv.weight"], s["conv.bias"], padding=1)
+        up = F.interpolate(x, scale_factor=2, mode="nearest")
+        if sr600:                                             # UpsampleSR600 drops the first and last row, util.py:799-801
+            up = up[..., 1:-1, :]
+        return F.conv2d(up, s["conv.weight"], s["conv.bias"], padding=1)
     if s.has("weight"):                                       # the first plain conv
         return F.conv2d(x, s["weight"], s["bias"], padding=1)
     raise KeyError(f"unrecognised block at {s.p}")
@@ -268,25 +278,47 @@ def _children(sd, prefix):
     return sorted(idx)
 
 
-def _unet_trunk(sd, x, emb, ctx, head_dim, batch):
-    """encoder / middle / decoder with skip concatenation, unet_t2v.py:257-277."""
+def fourier_filter(x, threshold, scale):
+    """Fourier_filter, unet_sr600.py:30-49: scale the (2*threshold)^2 centre bins of the shifted 2-D
+    spectrum of every [H, W] plane, keep the real part of the inverse transform."""
+    dtype = x.dtype
+    xf = torch.fft.fftshift(torch.fft.fftn(x.float(), dim=(-2, -1)), dim=(-2, -1))
+    hh, ww = xf.shape[-2:]
+    mask = torch.ones(xf.shape, dtype=torch.float32, device=x.device)
+    crow, ccol = hh // 2, ww // 2
+    mask[..., crow - threshold:crow + threshold, ccol - threshold:ccol + threshold] = scale
+    xf = torch.fft.ifftshift(xf * mask, dim=(-2, -1))
+    return torch.fft.ifftn(xf, dim=(-2, -1)).real.to(dtype)
+
+
+def _unet_trunk(sd, x, emb, ctx, head_dim, batch, woimg=False, conv_in_add=None, sr600=False):
+    """encoder / middle / decoder with skip concatenation, unet_t2v.py:257-277.
+    conv_in_add: tensor added right after the first conv (HiGen img_embedding, unet_higen.py:544-547);
+    sr600: backbone scaling + Fourier-filtered skips on the first two decoder blocks (unet_sr600.py:269-285)."""
     root = _SD(sd)
     skips = []
     for i in _children(sd, "input_blocks."):
         blk = root.sub(f"input_blocks.{i}")
         if blk.has("op.weight"):
-            x = _run_block(x, blk, emb, ctx, head_dim, batch)
+            x = _run_block(x, blk, emb, ctx, head_dim, batch, woimg, sr600)
         else:
             for j in _children(sd, blk.p):
-                x = _run_block(x, blk.sub(str(j)), emb, ctx, head_dim, batch)
+                x = _run_block(x, blk.sub(str(j)), emb, ctx, head_dim, batch, woimg, sr600)
+                if i == 0 and j == 0 and conv_in_add is not None:
+                    x = x + conv_in_add
         skips.append(x)
     for j in _children(sd, "middle_block."):
-        x = _run_block(x, root.sub(f"middle_block.{j}"), emb, ctx, head_dim, batch)
-    for i in _children(sd, "output_blocks."):
-        x = torch.cat([x, skips.pop()], dim=1)
+        x = _run_block(x, root.sub(f"middle_block.{j}"), emb, ctx, head_dim, batch, woimg)
+    for n, i in enumerate(_children(sd, "output_blocks.")):
+        skip = skips.pop()
+        if sr600 and n < 2:
+            half = x.shape[1] // 2
+            x = torch.cat([x[:, :half] * (1.1, 1.2)[n], x[:, half:]], dim=1)
+            skip = fourier_filter(skip, 1, (0.6, 0.4)[n])
+        x = torch.cat([x, skip], dim=1)
         blk = root.sub(f"output_blocks.{i}")
         for j in _children(sd, blk.p):
-            x = _run_block(x, blk.sub(str(j)), emb, ctx, head_dim, batch)
+            x = _run_block(x, blk.sub(str(j)), emb, ctx, head_dim, batch, woimg, sr600)
     x = F.conv2d(F.silu(_gn(x, root.sub("out.0"), 1e-5)), sd["out.2.weight"], sd["out.2.bias"], padding=1)
     return x
 
@@ -307,6 +339,81 @@ def unet_t2v_forward(sd, x, t, y, fps=None, head_dim=64, use_fps_condition=False
     ctx = y.repeat_interleave(f, dim=0)
     xx = x.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
     out = _unet_trunk(sd, xx, emb, ctx, head_dim, b)
+    return out.reshape(b, f, -1, h, w).permute(0, 2, 1, 3, 4)
+
+
+def unet_videolcm_forward(sd, x, t, y, fps=None, head_dim=64, use_fps_condition=False):
+    """UNetSD_VideoLCM.forward with video_compositions == ['text'] (configs/videolcm_t2v_infer.yaml:67),
+    unet_videolcm.py:541-760: `concat` stays all-zero (:598), pre_image is an empty Sequential (:409,705),
+    the context is y alone (:713-726)."""
+    b, c, f, h, w = x.shape
+    dim = sd["time_embed.0.weight"].shape[1]
+    root = _SD(sd)
+    concat_dim = sd["input_blocks.0.0.weight"].shape[1] - c
+    xx = torch.cat([x, x.new_zeros(b, concat_dim, f, h, w)], dim=1)
+    emb = _mlp(sinusoidal_embedding(t, dim).to(x.dtype), root.sub("time_embed"))
+    if use_fps_condition and fps is not None:
+        emb = emb + _mlp(sinusoidal_embedding(fps, dim).to(x.dtype), root.sub("fps_embedding"))
+    emb = emb.repeat_interleave(f, dim=0)
+    ctx = y.repeat_interleave(f, dim=0)
+    xx = xx.permute(0, 2, 1, 3, 4).reshape(b * f, c + concat_dim, h, w)
+    out = _unet_trunk(sd, xx, emb, ctx, head_dim, b)
+    return out.reshape(b, f, -1, h, w).permute(0, 2, 1, 3, 4)
+
+
+def unet_sr600_forward(sd, x, t, y, head_dim=64):
+    """UNetSD_SR600.forward, unet_sr600.py:220-299."""
+    b, c, f, h, w = x.shape
+    dim = sd["time_embed.0.weight"].shape[1]
+    emb = _mlp(sinusoidal_embedding(t, dim).to(x.dtype), _SD(sd).sub("time_embed")).repeat_interleave(f, dim=0)
+    ctx = y.repeat_interleave(f, dim=0)
+    xx = x.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+    out = _unet_trunk(sd, xx, emb, ctx, head_dim, b, sr600=True)
+    return out.reshape(b, f, -1, h, w).permute(0, 2, 1, 3, 4)
+
+
+def _context_block_higen(x, ctx, s, heads):
+    """BasicTransformerBlock with disable_self_attn=True (util.py:700-704): attn1 is cross attention too."""
+    x = _attention(_ln(x, s.sub("norm1")), ctx, s.sub("attn1"), heads) + x
+    x = _attention(_ln(x, s.sub("norm2")), ctx, s.sub("attn2"), heads) + x
+    h = _ln(x, s.sub("norm3"))
+    val, gate = _lin(h, s.sub("ff.net.0.proj")).chunk(2, dim=-1)
+    return _lin(val * F.gelu(gate), s.sub("ff.net.2")) + x
+
+
+def unet_higen_forward(sd, x, t, y, spat_prior, motion_cond, appearance_cond, fps=None, head_dim=64,
+                       use_fps_condition=False):
+    """UNetSD_HiGen.forward, unet_higen.py:401-467.
+    embeddings (:436-443): per-frame time + motion (:387-396, linear interpolation of f-1 embeddings to f
+    frames) + appearance (:398-399); context (:444-445): TextContextCrossTransformerMultiLayer :154-172;
+    spat_prior enters through img_embedding right after the first conv (:544-547)."""
+    b, c, f, h, w = x.shape
+    dim = sd["time_embed.0.weight"].shape[1]
+    root = _SD(sd)
+    emb = _mlp(sinusoidal_embedding(t, dim).to(x.dtype), root.sub("time_embed"))
+    if use_fps_condition and fps is not None:
+        emb = emb + _mlp(sinusoidal_embedding(fps, dim).to(x.dtype), root.sub("fps_embedding"))
+    emb = emb.repeat_interleave(f, dim=0)
+    if f > 1:
+        if motion_cond.size(1) != f:
+            me = sinusoidal_embedding(motion_cond.flatten(0, 1), dim).view(b, f - 1, dim)
+            me = F.interpolate(me.transpose(1, 2), size=f, mode="linear").transpose(1, 2)
+        else:
+            me = sinusoidal_embedding(motion_cond.flatten(0, 1), dim).view(b, f, dim)
+        me = _mlp(me.to(x.dtype), root.sub("msim_embedding")).flatten(0, 1)
+    else:
+        me = _mlp(sinusoidal_embedding(motion_cond, dim).to(x.dtype), root.sub("msim_embedding"))
+    emb = emb + me
+    emb = emb + _mlp(appearance_cond.to(x.dtype), root.sub("asim_embedding")).flatten(0, 1)
+    ce = root.sub("context_embedding")
+    yy = _lin(y, ce.sub("input_mapping"))
+    tok = sd["context_embedding.tokens"].to(x.dtype).repeat(b, 1, 1)
+    for d in _children(sd, "context_embedding.context_transformer."):
+        tok = _context_block_higen(tok, yy, ce.sub(f"context_transformer.{d}"), 8)
+    ctx = _lin(tok, ce.sub("output_mapping")).repeat_interleave(f, dim=0)
+    img = F.conv2d(spat_prior, sd["img_embedding.weight"], sd["img_embedding.bias"], padding=1).repeat_interleave(f, dim=0)
+    xx = x.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+    out = _unet_trunk(sd, xx, emb, ctx, head_dim, b, woimg=True, conv_in_add=img)
     return out.reshape(b, f, -1, h, w).permute(0, 2, 1, 3, 4)
 
 

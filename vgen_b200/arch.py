@@ -31,7 +31,7 @@ class Layer:
 
 @dataclass
 class UNetPlan:
-    kind: str                               # t2v | i2vgen
+    kind: str                               # t2v | i2vgen | videolcm | sr600 | higen
     in_dim: int
     dim: int
     embed_dim: int
@@ -42,6 +42,7 @@ class UNetPlan:
     num_tokens: int
     concat_dim: int
     use_fps_condition: bool
+    context_embedding_depth: int = 0        # higen: depth of TextContextCrossTransformerMultiLayer
     input_blocks: List[List[Layer]] = field(default_factory=list)
     middle: List[Layer] = field(default_factory=list)
     output_blocks: List[List[Layer]] = field(default_factory=list)
@@ -49,7 +50,7 @@ class UNetPlan:
 
 def unet_plan(kind, in_dim=4, dim=512, y_dim=512, context_dim=512, out_dim=6, num_tokens=4, dim_mult=(1, 2, 3, 4),
               num_heads=None, head_dim=64, num_res_blocks=3, attn_scales=(1 / 2, 1 / 4, 1 / 8), temporal_attention=True,
-              use_fps_condition=False, concat_dim=8, **_ignored) -> UNetPlan:
+              use_fps_condition=False, concat_dim=8, context_embedding_depth=4, **_ignored) -> UNetPlan:
     """Block layout for the given constructor kwargs (defaults are the reference's own)."""
     if not temporal_attention:
         raise NotImplementedError("temporal_attention=False is not on the sampling hot path")
@@ -58,13 +59,17 @@ def unet_plan(kind, in_dim=4, dim=512, y_dim=512, context_dim=512, out_dim=6, nu
     if kind == "i2vgen":
         concat_dim = in_dim  # unet_i2vgen.py:82 overrides the argument
         use_fps_condition = True  # fps_embedding is always built and used (unet_i2vgen.py:104-109,298)
+    if kind == "sr600":
+        use_fps_condition = False  # UNetSD_SR600 never builds fps_embedding (unet_sr600.py:96-100)
+    has_concat = kind in ("i2vgen", "videolcm")  # channels concatenated to x before the first conv
     plan = UNetPlan(kind, in_dim, dim, embed_dim, y_dim, context_dim, out_dim, head_dim, num_tokens,
-                    concat_dim if kind == "i2vgen" else 0, use_fps_condition)
+                    concat_dim if has_concat else 0, use_fps_condition,
+                    context_embedding_depth if kind == "higen" else 0)
     enc_dims = [dim * u for u in [1] + list(dim_mult)]
     dec_dims = [dim * u for u in [dim_mult[-1]] + list(dim_mult)[::-1]]
     shortcut = []
     scale = 1.0
-    first_in = in_dim + (plan.concat_dim if kind == "i2vgen" else 0)
+    first_in = in_dim + plan.concat_dim
     plan.input_blocks.append([
         Layer("conv_in", "input_blocks.0.0.", first_in, dim),
         Layer("temporal", "input_blocks.0.1.", dim, dim, num_heads, num_heads * head_dim),
@@ -185,6 +190,15 @@ def unet_spec(plan: UNetPlan) -> Spec:
             _conv("local_image_embedding.5.", 1024, cd * 16, 3, 3)
     elif plan.use_fps_condition:
         s += _mlp("fps_embedding.", plan.dim, plan.embed_dim, plan.embed_dim)
+    if plan.kind == "higen":
+        # TextContextCrossTransformerMultiLayer (unet_higen.py:154-166) + similarity / image embeddings (:271-289)
+        ed = plan.embed_dim
+        s += [("context_embedding.tokens", (1, plan.num_tokens, ed))]
+        for d in range(plan.context_embedding_depth):
+            s += _basic_block(f"context_embedding.context_transformer.{d}.", ed, ed)
+        s += _lin("context_embedding.input_mapping.", ed, plan.y_dim) + _lin("context_embedding.output_mapping.", plan.context_dim, ed)
+        s += _mlp("asim_embedding.", 32, ed, ed) + _mlp("msim_embedding.", plan.dim, ed, ed)
+        s += _conv("img_embedding.", plan.dim, plan.in_dim, 3, 3)
     for blk in plan.input_blocks:
         for L in blk:
             s += _layer_spec(L, plan)
@@ -205,6 +219,8 @@ def unet_zero_init(name: str) -> bool:
         return True
     if ".out_layers.3." in name or ".temopral_conv.conv4.3." in name:
         return True
+    if name.startswith(("asim_embedding.2.", "msim_embedding.2.", "img_embedding.")):
+        return True  # unet_higen.py:276-289
     return name == "out.2.weight" or name.startswith("fps_embedding.2.")
 
 

@@ -52,6 +52,11 @@ _SIGNATURES = {
     "vgen_attention_d64": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "vgen_attention_temporal": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "vgen_softmax_rows": [_vp, _i64, _i64, _i64, _f32, _vp],
+    "vgen_attention_cross_small": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
+    "vgen_interp_linear_rows": [_vp, _vp, _i64, _i64, _i64, _i64, _vp],
+    "vgen_fourier_lowfreq_filter": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
+    "vgen_upsample_nearest2x_rows": [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp],
+    "vgen_scale_copy2d": [_vp, _i64, _vp, _i64, _i64, _i64, _f32, _vp],
     "vgen_cp_to_pc": [_vp, _i32, _vp, _i64, _i64, _i64, _i64, _vp],
     "vgen_pc_to_cp": [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp],
     "vgen_im2col": [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp],

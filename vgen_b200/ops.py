@@ -289,6 +289,63 @@ def attention_temporal(q, k, v, heads, head_dim, out=None):
     return out
 
 
+def attention_cross_small(q, k, v, heads, kv_batch_div=1, out=None):
+    """q [b, lq, heads*d], k/v [b // kv_batch_div, lk, heads*d] for any d <= 256 (tiny problems only)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk16(t, nm)
+        if t.dim() != 3 or t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise _l.VgenError(f"attention_cross_small: {nm} must be [b, l, h*d] with dense batch stride")
+    b, lq, inner = q.shape
+    lk = k.shape[1]
+    d = inner // heads
+    if inner != heads * d or k.shape[2] != inner or v.shape != k.shape or k.shape[0] * kv_batch_div != b:
+        raise _l.VgenError("attention_cross_small: shape mismatch")
+    if out is None:
+        out = torch.empty(b, lq, inner, device=q.device, dtype=torch.float16)
+    rc = _l.load().vgen_attention_cross_small(_p(q), _p(k), _p(v), _p(out), b, heads, lq, lk, d, q.stride(1), k.stride(1),
+                                              v.stride(1), out.stride(1), kv_batch_div, d ** -0.5, _stream())
+    _l.check(rc, "vgen_attention_cross_small")
+    return out
+
+
+def interp_linear_rows(x, lout):
+    """x [nseq, lin, c] fp16 -> [nseq, lout, c] (F.interpolate mode='linear' over the middle axis)."""
+    _chk16(x, "x")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise _l.VgenError("interp_linear_rows: x must be contiguous [nseq, lin, c]")
+    nseq, lin, c = x.shape
+    y = torch.empty(nseq, lout, c, device=x.device, dtype=torch.float16)
+    rc = _l.load().vgen_interp_linear_rows(_p(x), _p(y), nseq, lin, lout, c, _stream())
+    _l.check(rc, "vgen_interp_linear_rows")
+    return y
+
+
+def fourier_lowfreq_filter(x, scale, out=None):
+    """Fourier_filter(threshold=1) on channels-last x [nimg, h, w, c]; `out` may be a channel slice of a
+    wider channels-last buffer."""
+    _chk16(x, "x")
+    nimg, h, w, c = x.shape
+    x2, ldx = _rows_view(x, "x")
+    if out is None:
+        out = torch.empty(nimg, h, w, c, device=x.device, dtype=torch.float16)
+    o2, ldo = _rows_view(out, "out")
+    if o2.shape != x2.shape:
+        raise _l.VgenError("fourier_lowfreq_filter: shape mismatch")
+    rc = _l.load().vgen_fourier_lowfreq_filter(_p(x2), ldx, _p(o2), ldo, nimg, h, w, c, float(scale), _stream())
+    _l.check(rc, "vgen_fourier_lowfreq_filter")
+    return out
+
+
+def scale_copy2d(src, dst, s):
+    s2, lds = _rows_view(src, "src")
+    d2, ldd = _rows_view(dst, "dst")
+    if s2.shape != d2.shape:
+        raise _l.VgenError("scale_copy2d: shape mismatch")
+    rc = _l.load().vgen_scale_copy2d(_p(s2), lds, _p(d2), ldd, s2.shape[0], s2.shape[1], float(s), _stream())
+    _l.check(rc, "vgen_scale_copy2d")
+    return dst
+
+
 def softmax_rows_(x, scale=1.0):
     _chk16(x, "x")
     x2, ld = _rows_view(x, "x")
@@ -336,6 +393,16 @@ def upsample_nearest2x(x):
     y = torch.empty(nimg, 2 * h, 2 * w, c, device=x.device, dtype=torch.float16)
     rc = _l.load().vgen_upsample_nearest2x(_p(x), _p(y), nimg, h, w, c, _stream())
     _l.check(rc, "vgen_upsample_nearest2x")
+    return y
+
+
+def upsample_nearest2x_rows(x, row0, rows_out):
+    """nearest x2 upsampling keeping rows [row0, row0+rows_out) (UpsampleSR600 crops one row each side)."""
+    _chk16(x, "x")
+    nimg, h, w, c = x.shape
+    y = torch.empty(nimg, rows_out, 2 * w, c, device=x.device, dtype=torch.float16)
+    rc = _l.load().vgen_upsample_nearest2x_rows(_p(x), _p(y), nimg, h, w, c, row0, rows_out, _stream())
+    _l.check(rc, "vgen_upsample_nearest2x_rows")
     return y
 
 
