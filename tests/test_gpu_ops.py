@@ -18,7 +18,7 @@ def _checks():
     return mod
 
 
-@pytest.mark.parametrize("group", ["tapgemm", "tapgemm_1cta", "tapgemm_2cta", "tapgemm_simt", "norm", "attention", "elementwise"])
+@pytest.mark.parametrize("group", ["tapgemm", "tapgemm_1cta", "tapgemm_2cta", "tapgemm_simt", "norm", "attention", "elementwise", "variants"])
 def test_op_group(group):
     import torch
     mod = _checks()

@@ -21,6 +21,7 @@ import torch
 import vgen_b200
 from oracle import synth, vgen_oracle as vo
 from oracle.cases import CASES, make_inputs
+from _helpers import build_product, oracle_call, product_call
 
 pytestmark = pytest.mark.gpu
 
@@ -37,8 +38,7 @@ def _setup(golden_dir, name):
     spec = [(k, tuple(s)) for k, s in json.load(open(os.path.join(golden_dir, f"{name}.spec.json")))]
     sd = synth.state_dict(spec, seed=case["seed"])
     gold = np.load(os.path.join(golden_dir, f"{name}.npz"))
-    cls = {"t2v": vgen_b200.UNetSD_T2VBase, "i2vgen": vgen_b200.UNetSD_I2VGen, "vae": vgen_b200.AutoencoderKL}[case["kind"]]
-    m = cls(**case["ctor"])
+    m = build_product(case)
     m.load_state_dict(sd, strict=True)
     m = m.cuda().eval()
     inp = {k: v.cuda() for k, v in make_inputs(case).items()}
@@ -47,16 +47,11 @@ def _setup(golden_dir, name):
 
 
 def _fns(case, m, inp, sdg):
-    k = case["kind"]
-    if k == "t2v":
-        return (lambda: m(inp["x"], inp["t"], y=inp["y"])), (lambda: vo.unet_t2v_forward(sdg, inp["x"], inp["t"], inp["y"]))
-    if k == "i2vgen":
-        return (lambda: m(inp["x"], inp["t"], y=inp["y"], image=inp["image"], local_image=inp["local_image"], fps=inp["fps"])), \
-            (lambda: vo.unet_i2vgen_forward(sdg, inp["x"], inp["t"], inp["y"], inp["image"], inp["local_image"], inp["fps"]))
-    return (lambda: m.decode(inp["z"])), (lambda: vo.vae_decode(sdg, inp["z"]))
+    return (lambda: product_call(case, m, inp)), (lambda: oracle_call(case, sdg, inp))
 
 
-@pytest.mark.parametrize("name", ["t2v_tiny", "t2v_tiny_b2", "i2vgen_tiny", "vae_tiny"])
+@pytest.mark.parametrize("name", ["t2v_tiny", "t2v_tiny_b2", "i2vgen_tiny", "videolcm_tiny", "sr600_tiny", "higen_tiny",
+                                  "higen_tiny_f1", "vae_tiny"])
 def test_forward_parity(golden_dir, name):
     case, m, inp, sdg, gold = _setup(golden_dir, name)
     mine_fn, oracle_fn = _fns(case, m, inp, sdg)

@@ -14,6 +14,7 @@ import torch
 import vgen_b200
 from oracle import synth, vgen_oracle as vo
 from oracle.cases import CASES, FULL_CTORS
+from _helpers import build_product
 from vgen_b200 import arch, lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -37,13 +38,14 @@ def test_full_size_tensor_counts(golden_dir):
     assert len(_gold_spec(golden_dir, "full_t2v")) == 1480
     assert len(_gold_spec(golden_dir, "full_i2vgen")) == 1509
     assert len(_gold_spec(golden_dir, "full_vae")) == 248
+    assert len(_gold_spec(golden_dir, "full_videolcm")) == 1480 and len(_gold_spec(golden_dir, "full_sr600")) == 1480
+    assert len(_gold_spec(golden_dir, "full_higen")) == 1535
 
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_strict_state_dict_roundtrip(golden_dir, name):
     case = CASES[name]
-    cls = {"t2v": vgen_b200.UNetSD_T2VBase, "i2vgen": vgen_b200.UNetSD_I2VGen, "vae": vgen_b200.AutoencoderKL}[case["kind"]]
-    m = cls(**case["ctor"])
+    m = build_product(case)
     spec = _gold_spec(golden_dir, name)
     assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == spec
     sd = synth.state_dict(spec, seed=case["seed"])

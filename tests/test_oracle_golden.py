@@ -10,6 +10,7 @@ import torch
 
 from oracle import synth, vgen_oracle as vo
 from oracle.cases import CASES, make_inputs
+from _helpers import oracle_call
 
 
 def _load(golden_dir, name):
@@ -36,17 +37,12 @@ def test_schedules_bit_exact(golden_dir):
     assert vo.ddim_steps(1000, 50)[:2].tolist() == [981, 961] and vo.ddim_steps(1000, 4).tolist() == [751, 501, 251, 1]
 
 
-@pytest.mark.parametrize("name", ["t2v_tiny", "t2v_tiny_b2", "i2vgen_tiny", "vae_tiny"])
+@pytest.mark.parametrize("name", list(CASES))
 def test_oracle_matches_reference_golden(golden_dir, name):
     torch.set_grad_enabled(False)
     case, sd, gold = _load(golden_dir, name)
     inp = make_inputs(case)
-    if case["kind"] == "t2v":
-        out = vo.unet_t2v_forward(sd, inp["x"], inp["t"], inp["y"])
-    elif case["kind"] == "i2vgen":
-        out = vo.unet_i2vgen_forward(sd, inp["x"], inp["t"], inp["y"], inp["image"], inp["local_image"], inp["fps"])
-    else:
-        out = vo.vae_decode(sd, inp["z"])
+    out = oracle_call(case, sd, inp)
     ref = torch.from_numpy(gold["out"])
     assert out.shape == ref.shape
     assert float(ref.std()) > 0.1, "golden output must not be degenerate (zero-init trap)"
@@ -74,3 +70,24 @@ def test_oracle_vae_encode_matches_reference_golden(golden_dir):
     torch.manual_seed(case["encode"]["torch_seed"])       # the reference draws the posterior noise on the CPU generator
     z = vo.vae_encode_first_stage(sd, inp["img"], 0.18215)
     assert _maxrel(z, torch.from_numpy(gold["encode_z"])) < 5e-5
+
+
+def test_fourier_filter_is_a_four_bin_update():
+    """The SR600 skip filter only touches the 2x2 centre block of the shifted spectrum: the restated FFT
+    filter equals x - (1-s) * Re(inverse DFT of the bins (ky, kx) in {0,-1}^2) -- the identity the CUDA
+    kernel relies on (vgen_b200/csrc/variants.cu) -- for even and odd plane sizes."""
+    torch.manual_seed(3)
+    for hh, ww in ((5, 6), (12, 20), (7, 9), (2, 2)):
+        x = torch.randn(2, 3, hh, ww, dtype=torch.float64)
+        ref = vo.fourier_filter(x.float(), 1, 0.4).double()
+        yy = torch.arange(hh, dtype=torch.float64).view(hh, 1) / hh
+        xx = torch.arange(ww, dtype=torch.float64).view(1, ww) / ww
+        low = torch.zeros_like(x)
+        for ky in (0, -1):
+            for kx in (0, -1):
+                ph = 2 * np.pi * (ky * yy + kx * xx)
+                basis = torch.complex(torch.cos(ph), torch.sin(ph))
+                coef = (x * basis.conj()).sum(dim=(-2, -1), keepdim=True)
+                low = low + (coef * basis).real
+        mine = x - (1 - 0.4) * low / (hh * ww)
+        assert float((mine - ref).abs().max()) < 1e-5

@@ -23,6 +23,21 @@ def test_unet_t2v_against_reference_class():
     assert _maxrel(vo.unet_t2v_forward(sd, inp["x"], inp["t"], inp["y"]), m(inp["x"], inp["t"], y=inp["y"])) < 2e-5
 
 
+@pytest.mark.parametrize("name", ["videolcm_tiny", "sr600_tiny", "higen_tiny", "higen_tiny_f1"])
+def test_unet_variants_against_reference_classes(name):
+    """a21 variants, with weights from a seed the golden files do not use."""
+    from oracle.make_golden import build_variant
+    from _helpers import oracle_call, product_call
+    torch.set_grad_enabled(False)
+    ref = refload.load()
+    case = CASES[name]
+    m = build_variant(ref, case["kind"], case["ctor"]).eval()
+    sd = synth.state_dict(synth.spec_of(m), seed=78)
+    m.load_state_dict(sd, strict=True)
+    inp = make_inputs(case)
+    assert _maxrel(oracle_call(case, sd, inp), product_call(case, m, inp)) < 2e-5
+
+
 def test_default_init_is_degenerate_and_synth_is_not():
     """SURVEY.md section 8c hygiene: with the reference's default init the output is a per-channel constant."""
     torch.set_grad_enabled(False)

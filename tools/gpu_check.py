@@ -368,7 +368,68 @@ def group_elementwise():
     run_case("ddim", f)
 
 
+def group_variants():
+    """Kernels of the a21 model variants (variants.cu) against torch fp32 references of the reference ops."""
+    from vgen_b200 import ops
+    F = torch.nn.functional
+    g = torch.Generator(device="cpu").manual_seed(5)
+
+    def rnd(*s, scale=1.0):
+        return (torch.randn(*s, generator=g) * scale).cuda()
+
+    for (b, heads, lq, lk, d, div) in [(2, 8, 16, 77, 160, 1), (1, 8, 3, 5, 32, 1), (4, 2, 7, 9, 256, 2), (1, 1, 1, 1, 8, 1)]:
+        def f():
+            inner = heads * d
+            q = rnd(b, lq, inner).half()
+            kv = rnd(b // div, lk, 2 * inner).half()
+            k, v = kv[:, :, :inner], kv[:, :, inner:]
+            out = ops.attention_cross_small(q, k, v, heads, kv_batch_div=div)
+            sp = lambda t: t.float().reshape(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3)  # noqa: E731
+            kk, vv = k.repeat_interleave(div, 0), v.repeat_interleave(div, 0)
+            ref = F.scaled_dot_product_attention(sp(q), sp(kk), sp(vv)).permute(0, 2, 1, 3).reshape(b, lq, inner)
+            report(f"attention_cross_small b{b} h{heads} lq{lq} lk{lk} d{d} div{div}", rel_err(out, ref), 2e-3)
+        run_case(f"attn_small {b} {heads} {lq} {lk} {d}", f)
+
+    for (nseq, lin, lout, c) in [(2, 31, 32, 320), (1, 2, 3, 64), (3, 7, 16, 20), (1, 1, 4, 8)]:
+        def f():
+            x = rnd(nseq, lin, c).half()
+            out = ops.interp_linear_rows(x, lout)
+            ref = F.interpolate(x.float().transpose(1, 2), size=lout, mode="linear").transpose(1, 2)
+            report(f"interp_linear_rows {nseq}x{lin}->{lout} c{c}", rel_err(out, ref), 1e-3)
+        run_case(f"interp {nseq} {lin} {lout}", f)
+
+    def fft_filter(x_nchw, scale):
+        xf = torch.fft.fftshift(torch.fft.fftn(x_nchw.float(), dim=(-2, -1)), dim=(-2, -1))
+        hh, ww = xf.shape[-2:]
+        mask = torch.ones_like(xf.real)
+        mask[..., hh // 2 - 1:hh // 2 + 1, ww // 2 - 1:ww // 2 + 1] = scale
+        return torch.fft.ifftn(torch.fft.ifftshift(xf * mask, dim=(-2, -1)), dim=(-2, -1)).real
+
+    for (n, h, w, c, scale) in [(3, 5, 6, 128, 0.6), (32, 12, 20, 1280, 0.4), (2, 7, 9, 100, 0.6), (1, 2, 2, 64, 0.4)]:
+        def f():
+            x = (rnd(n, h, w, c) + 0.7).half()
+            wide = torch.zeros(n, h, w, c + 64, device="cuda", dtype=torch.float16)
+            ops.fourier_lowfreq_filter(x, scale, out=wide.view(-1, c + 64)[:, 32:32 + c])
+            ref = fft_filter(x.permute(0, 3, 1, 2), scale).permute(0, 2, 3, 1)
+            report(f"fourier_lowfreq {n}x{h}x{w} c{c} s{scale}", rel_err(wide[..., 32:32 + c], ref), 1e-3)
+            report(f"fourier_lowfreq {n}x{h}x{w} c{c} untouched columns", float(wide[..., :32].abs().max() + wide[..., 32 + c:].abs().max()), 0.0)
+        run_case(f"fourier {n} {h} {w} {c}", f)
+
+    def f():
+        x = rnd(3, 5, 7, 64).half()
+        out = ops.upsample_nearest2x_rows(x, 1, 8)
+        ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest")[..., 1:-1, :].permute(0, 2, 3, 1)
+        report("upsample_nearest2x_rows crop 1", rel_err(out, ref), 0.0)
+        src = rnd(100, 96).half()
+        dst = torch.zeros(100, 200, device="cuda", dtype=torch.float16)
+        ops.scale_copy2d(src[:, :40], dst[:, 8:48], 1.1)
+        report("scale_copy2d", rel_err(dst[:, 8:48], (src[:, :40] * 1.1)), 0.0)
+        report("scale_copy2d untouched", float(dst[:, :8].abs().max() + dst[:, 48:].abs().max()), 0.0)
+    run_case("upsample_rows/scale_copy", f)
+
+
 GROUPS = {
+    "variants": group_variants,
     "tapgemm": group_tapgemm,
     "tapgemm_simt": group_tapgemm_simt,
     "tapgemm_1cta": group_tapgemm_1cta,

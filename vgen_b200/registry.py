@@ -57,11 +57,12 @@ USING_REFERENCE_REGISTRY = False
 
 
 def register(force_local: bool = False):
-    """Register UNetSD_T2VBase, UNetSD_I2VGen, DiffusionDDIM, AutoencoderKL.  Returns the three registries."""
+    """Register the UNets (T2VBase, I2VGen, VideoLCM, SR600, HiGen), DiffusionDDIM and AutoencoderKL under the
+    reference's registry names.  Returns the three registries."""
     global MODEL, DIFFUSION, AUTO_ENCODER, USING_REFERENCE_REGISTRY
     from .autoencoder import AutoencoderKL
     from .diffusion import DiffusionDDIM
-    from .unet import UNetSD_I2VGen, UNetSD_T2VBase
+    from .unet import UNetSD_HiGen, UNetSD_I2VGen, UNetSD_SR600, UNetSD_T2VBase, UNetSD_VideoLCM
 
     regs = None
     if not force_local:
@@ -77,7 +78,7 @@ def register(force_local: bool = False):
     MODEL, DIFFUSION, AUTO_ENCODER = regs
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # replacing the reference classes is the point
-        for cls in (UNetSD_T2VBase, UNetSD_I2VGen):
+        for cls in (UNetSD_T2VBase, UNetSD_I2VGen, UNetSD_VideoLCM, UNetSD_SR600, UNetSD_HiGen):
             MODEL.register_class()(cls)
         DIFFUSION.register_class()(DiffusionDDIM)
         AUTO_ENCODER.register_class()(AutoencoderKL)

@@ -59,14 +59,17 @@ class _Weights:
 
 class _UNetBase(SpecModule):
     KIND = "t2v"
+    WOIMG = False     # HiGen: temporal branches contribute 0 when a single frame is sampled
+    SR600 = False     # SR600: (2,1)-padded downsampling, row-cropped upsampling, filtered skips
 
     def __init__(self, config=None, in_dim=4, dim=512, y_dim=512, context_dim=512, hist_dim=156, dim_condition=4,
                  out_dim=6, num_tokens=4, dim_mult=[1, 2, 3, 4], num_heads=None, head_dim=64, num_res_blocks=3,
                  attn_scales=[1 / 2, 1 / 4, 1 / 8], use_scale_shift_norm=True, dropout=0.1, temporal_attn_times=1,
                  temporal_attention=True, use_checkpoint=False, use_image_dataset=False, use_sim_mask=False,
                  training=True, inpainting=True, use_fps_condition=False, p_all_zero=0.1, p_all_keep=0.1, zero_y=None,
-                 adapter_transformer_layers=1, concat_dim=8, **kwargs):
+                 adapter_transformer_layers=1, concat_dim=8, context_embedding_depth=4, **kwargs):
         super().__init__()
+        self.cfg = config
         if head_dim != 64:
             raise NotImplementedError("vgen_b200: head_dim must be 64 (all released VGen checkpoints)")
         if use_image_dataset:
@@ -77,7 +80,7 @@ class _UNetBase(SpecModule):
                                    num_tokens=num_tokens, dim_mult=tuple(dim_mult), num_heads=num_heads, head_dim=head_dim,
                                    num_res_blocks=num_res_blocks, attn_scales=tuple(attn_scales),
                                    temporal_attention=temporal_attention, use_fps_condition=use_fps_condition,
-                                   concat_dim=concat_dim)
+                                   concat_dim=concat_dim, context_embedding_depth=context_embedding_depth)
         # attributes the reference exposes and engines read
         self.in_dim, self.dim, self.y_dim, self.context_dim, self.out_dim = in_dim, dim, y_dim, context_dim, out_dim
         self.embed_dim, self.num_tokens, self.head_dim = dim * 4, num_tokens, head_dim
@@ -112,9 +115,13 @@ class _UNetBase(SpecModule):
             W[p + "w"] = _f16(w[:, :, :, 0, 0].permute(0, 2, 1).reshape(w.shape[0], -1), dev)
             W[p + "b"] = _f32(sd[p + "bias"], dev)
 
-        def block(p, cross):
+        def block(p, cross, cross1=False):
             a1, a2 = p + "attn1.", p + "attn2."
-            W[a1 + "qkv"] = _f16(torch.cat([sd[a1 + "to_q.weight"], sd[a1 + "to_k.weight"], sd[a1 + "to_v.weight"]], 0), dev)
+            if cross1:   # disable_self_attn=True: attn1 attends to the context as well (util.py:700-702)
+                W[a1 + "q"] = _f16(sd[a1 + "to_q.weight"], dev)
+                W[a1 + "kv"] = _f16(torch.cat([sd[a1 + "to_k.weight"], sd[a1 + "to_v.weight"]], 0), dev)
+            else:
+                W[a1 + "qkv"] = _f16(torch.cat([sd[a1 + "to_q.weight"], sd[a1 + "to_k.weight"], sd[a1 + "to_v.weight"]], 0), dev)
             lin(a1 + "to_out.0.")
             if cross:
                 W[a2 + "q"] = _f16(sd[a2 + "to_q.weight"], dev)
@@ -133,7 +140,7 @@ class _UNetBase(SpecModule):
         def layer(L):
             p = L.prefix
             if L.kind == "conv_in":
-                conv3(p, cin_pad=8 if L.cin < 8 else None)
+                conv3(p, cin_pad=((L.cin + 7) // 8) * 8)
             elif L.kind == "res":
                 norm(p + "in_layers.0."), conv3(p + "in_layers.2.")
                 lin(p + "emb_layers.1.")
@@ -163,6 +170,14 @@ class _UNetBase(SpecModule):
             norm(e + "0.norm."), lin(e + "0.fn.to_qkv.", bias=False), lin(e + "0.fn.to_out.0.")
             lin(e + "1.net.0.0."), lin(e + "1.net.2.")
             conv3("local_image_embedding.0.", cin_pad=8), conv3("local_image_embedding.3."), conv3("local_image_embedding.5.")
+        if self.KIND == "higen":
+            W["context_embedding.tokens"] = _f16(sd["context_embedding.tokens"][0], dev)
+            for d in range(self.plan.context_embedding_depth):
+                block(f"context_embedding.context_transformer.{d}.", True, cross1=True)
+            lin("context_embedding.input_mapping."), lin("context_embedding.output_mapping.")
+            for pre in ("asim_embedding.", "msim_embedding."):
+                lin(pre + "0."), lin(pre + "2.")
+            conv3("img_embedding.", cin_pad=8)
         for blk in self.plan.input_blocks:
             for L in blk:
                 layer(L)
@@ -186,26 +201,30 @@ class _UNetBase(SpecModule):
         out = ops.linear(col, wt, bias=W[p + "b"], residual=epi.get("residual"))
         return out.view(n, h, w, wt.shape[0])
 
-    def _conv3x3_s2(self, x, W, p, act_silu=False):
+    def _conv3x3_s2(self, x, W, p, act_silu=False, pad_h=1):
         n, h, w, c = x.shape
-        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        ho, wo = (h + 2 * pad_h - 3) // 2 + 1, (w - 1) // 2 + 1
         wt = W[p + "w"]
-        col = ops.im2col(x, 3, 3, 2, 1, 1, ho, wo, wt.shape[1], act_silu=act_silu)
+        col = ops.im2col(x, 3, 3, 2, pad_h, 1, ho, wo, wt.shape[1], act_silu=act_silu)
         return ops.linear(col, wt, bias=W[p + "b"]).view(n, ho, wo, wt.shape[0])
 
     def _res_block(self, x, emb, L, W, b, f):
         """ResBlock._forward + TemporalConvBlock_v2 (util.py:900-927,1686-1697)."""
         p = L.prefix
         n, h, w, _ = x.shape
-        e = ops.linear_small(emb, W[p + "emb_layers.1.w"], W[p + "emb_layers.1.b"], silu_in=True)  # [b, cout]
+        # emb is [b, E] (one embedding per video) or [b*f, E] (HiGen: one per frame, unet_higen.py:440-443)
+        e = ops.linear_small(emb, W[p + "emb_layers.1.w"], W[p + "emb_layers.1.b"], silu_in=True)  # [b | b*f, cout]
         g = ops.group_norm(x, W[p + "in_layers.0.g"], W[p + "in_layers.0.b"], 1e-5, True)
-        hcur = ops.conv2d_3x3(g, W[p + "in_layers.2.w"], bias=W[p + "in_layers.2.b"], group_bias=e, group_div=f)
+        hcur = ops.conv2d_3x3(g, W[p + "in_layers.2.w"], bias=W[p + "in_layers.2.b"], group_bias=e,
+                              group_div=(b * f) // emb.shape[0])
         g = ops.group_norm(hcur, W[p + "out_layers.0.g"], W[p + "out_layers.0.b"], 1e-5, True)
         if L.cin != L.cout:
             skip = ops.linear(x.view(-1, L.cin), W[p + "skip_connection.w"], bias=W[p + "skip_connection.b"])
         else:
             skip = x
         hcur = ops.conv2d_3x3(g, W[p + "out_layers.3.w"], bias=W[p + "out_layers.3.b"], residual=skip.view(-1, L.cout))
+        if self.WOIMG and f == 1:
+            return hcur  # TemporalConvBlock_v2WoImg: identity + 0.0 * branch (unet_higen.py:80-83)
         # temporal conv: GroupNorm statistics over all frames of a video, 3-tap conv over frames
         t = hcur
         names = (("conv1", 2), ("conv2", 3), ("conv3", 3), ("conv4", 3))
@@ -265,6 +284,8 @@ class _UNetBase(SpecModule):
     def _temporal_transformer(self, x, L, W, b, f):
         """TemporalTransformer.forward, only_self_att=True (util.py:1240-1286): both attentions are
         self-attention over the f frames of a pixel; GroupNorm statistics span all frames."""
+        if self.WOIMG and f == 1:
+            return x  # TemporalTransformerWoImg: 0.0 * branch + x_in (unet_higen.py:146-149)
         p = L.prefix
         n, h, w, c = x.shape
         hw, inner = h * w, L.inner
@@ -279,7 +300,7 @@ class _UNetBase(SpecModule):
         out = ops.linear(t, W[p + "proj_out.w"], bias=W[p + "proj_out.b"], residual=x.view(-1, c))
         return out.view(n, h, w, c)
 
-    def _run_layer(self, x, L, W, emb, ctx_tokens, b, f):
+    def _run_layer(self, x, L, W, emb, ctx_tokens, b, f, conv_in_residual=None):
         if L.kind == "res":
             return self._res_block(x, emb, L, W, b, f)
         if L.kind == "spatial":
@@ -287,24 +308,35 @@ class _UNetBase(SpecModule):
         if L.kind == "temporal":
             return self._temporal_transformer(x, L, W, b, f)
         if L.kind == "down":
-            return self._conv3x3_s2(x, W, L.prefix + "op.")
+            # UNetSD_SR600 pads the height by 2 (unet_sr600.py:151-153)
+            return self._conv3x3_s2(x, W, L.prefix + "op.", pad_h=2 if self.SR600 else 1)
         if L.kind == "up":
-            return ops.conv2d_3x3(ops.upsample_nearest2x(x), W[L.prefix + "conv.w"], bias=W[L.prefix + "conv.b"])
+            if self.SR600:   # UpsampleSR600 drops the first and last upsampled row (util.py:799-801)
+                up = ops.upsample_nearest2x_rows(x, 1, 2 * x.shape[1] - 2)
+            else:
+                up = ops.upsample_nearest2x(x)
+            return ops.conv2d_3x3(up, W[L.prefix + "conv.w"], bias=W[L.prefix + "conv.b"])
         if L.kind == "conv_in":
+            if conv_in_residual is not None:
+                return self._conv3x3_any(x, W, L.prefix, residual=conv_in_residual)
             return self._conv3x3_any(x, W, L.prefix)
         raise ValueError(L.kind)
 
-    def _trunk(self, x, emb, ctx_tokens, W, b, f):
+    def _merge_skip(self, x, skip, n):
+        """torch.cat([x, xs.pop()], dim=1) of the decoder (unet_t2v.py:269); SR600 overrides it."""
+        return ops.concat_channels(x, skip)
+
+    def _trunk(self, x, emb, ctx_tokens, W, b, f, conv_in_residual=None):
         """encoder / middle / decoder with skip concatenation + head (unet_t2v.py:257-277)."""
         skips = []
         for blk in self.plan.input_blocks:
             for L in blk:
-                x = self._run_layer(x, L, W, emb, ctx_tokens, b, f)
+                x = self._run_layer(x, L, W, emb, ctx_tokens, b, f, conv_in_residual)
             skips.append(x)
         for L in self.plan.middle:
             x = self._run_layer(x, L, W, emb, ctx_tokens, b, f)
-        for blk in self.plan.output_blocks:
-            x = ops.concat_channels(x, skips.pop())
+        for n, blk in enumerate(self.plan.output_blocks):
+            x = self._merge_skip(x, skips.pop(), n)
             for L in blk:
                 x = self._run_layer(x, L, W, emb, ctx_tokens, b, f)
         g = ops.group_norm(x, W["out.0.g"], W["out.0.b"], 1e-5, True)
@@ -442,4 +474,153 @@ class UNetSD_I2VGen(_UNetBase):
         xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=c + cd).view(-1, c + cd)
         ops.copy2d(concat, xin[:, c:])
         out = self._trunk(xin.view(b * f, h, w, c + cd), emb, ctx, W, b, f)
+        return ops.pc_to_cp(out.view(b, f * h * w, self.out_dim), b, self.out_dim, f * h * w).view(b, self.out_dim, f, h, w)
+
+
+class UNetSD_VideoLCM(_UNetBase):
+    """Drop-in for tools/modules/unet/unet_videolcm.py:188-189 (MODEL 'UNetSD_VideoLCM') on the text-to-video
+    path of configs/videolcm_t2v_infer.yaml (video_compositions == ['text']): `concat` stays all-zero
+    (:598), pre_image is an empty Sequential (:409,:705) and the context is the text tokens (:713-726).
+    The other compositions (depth / sketch / motion / ... adapters of the VideoComposer path) are outside
+    SURVEY.md section 8 and raise."""
+    KIND = "videolcm"
+
+    def __init__(self, config=None, *args, **kwargs):
+        comps = list(getattr(config, "video_compositions", None) or (config or {}).get("video_compositions", ["text"]))
+        if comps != ["text"]:
+            raise NotImplementedError(f"vgen_b200 UNetSD_VideoLCM: video_compositions {comps} != ['text'] is not on the hot path")
+        super().__init__(config, *args, **kwargs)
+        self.video_compositions = comps
+        self.concat_dim = self.plan.concat_dim
+
+    @torch.no_grad()
+    def forward(self, x, t, y=None, depth=None, image=None, motion=None, local_image=None, single_sketch=None,
+                masked=None, canny=None, sketch=None, histogram=None, fps=None, video_mask=None,
+                focus_present_mask=None, prob_focus_present=0., mask_last_frame_num=0, **kwargs):
+        self._check_x(x, t)
+        for name, v in (("depth", depth), ("image", image), ("motion", motion), ("local_image", local_image),
+                        ("single_sketch", single_sketch), ("masked", masked), ("canny", canny), ("sketch", sketch),
+                        ("histogram", histogram)):
+            if v is not None:
+                raise NotImplementedError(f"vgen_b200 UNetSD_VideoLCM: condition '{name}' is not on the text-only hot path")
+        W = self._packed or self._pack()
+        b, c, f, h, w = x.shape
+        emb = self._time_embedding(t, fps, W)
+        if y is None:
+            if self.zero_y is None:
+                raise ValueError("y is None and no zero_y was given")
+            y = self.zero_y.to(x.device).repeat(b, 1, 1)            # all tokens (:724-725), unlike T2VBase
+        ctx = self._to_f16_rows(y)
+        cin = self.plan.input_blocks[0][0].cin                      # in_dim + concat_dim; the concat channels are 0
+        cpad = ((cin + 7) // 8) * 8
+        xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=cpad).view(b * f, h, w, cpad)
+        out = self._trunk(xin, emb, ctx, W, b, f)
+        return ops.pc_to_cp(out.view(b, f * h * w, self.out_dim), b, self.out_dim, f * h * w).view(b, self.out_dim, f, h, w)
+
+
+class UNetSD_SR600(_UNetBase):
+    """Drop-in for tools/modules/unet/unet_sr600.py:52-53 (MODEL 'UNetSD_SR600'): the T2V trunk with
+    (2,1)-padded downsampling, row-cropped upsampling, and -- on the first two decoder blocks -- the
+    backbone half scaled by 1.1 / 1.2 and the skip passed through Fourier_filter(threshold=1, 0.6 / 0.4)
+    (:269-285).  The filter and the scaling are fused into the channel concat."""
+    KIND = "sr600"
+    SR600 = True
+    _BACKBONE_SCALE = (1.1, 1.2)
+    _SKIP_SCALE = (0.6, 0.4)
+
+    def _merge_skip(self, x, skip, n):
+        if n >= 2:
+            return ops.concat_channels(x, skip)
+        cx, cs = x.shape[-1], skip.shape[-1]
+        out = torch.empty(*x.shape[:-1], cx + cs, device=x.device, dtype=torch.float16)
+        o2, x2 = out.view(-1, cx + cs), x.view(-1, cx)
+        half = cx // 2
+        ops.scale_copy2d(x2[:, :half], o2[:, :half], self._BACKBONE_SCALE[n])
+        ops.copy2d(x2[:, half:], o2[:, half:cx])
+        ops.fourier_lowfreq_filter(skip, self._SKIP_SCALE[n], out=o2[:, cx:])
+        return out
+
+    @torch.no_grad()
+    def forward(self, x, t, y, x_lr=None, fps=None, video_mask=None, focus_present_mask=None, prob_focus_present=0.,
+                mask_last_frame_num=0, **kwargs):
+        self._check_x(x, t)
+        W = self._packed or self._pack()
+        b, c, f, h, w = x.shape
+        if h % 2:
+            raise ValueError("UNetSD_SR600: latent height must be even (UpsampleSR600 restores 2*h'-2 rows)")
+        emb = self._time_embedding(t, None, W)
+        ctx = self._to_f16_rows(y)
+        xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=8).view(b * f, h, w, 8)
+        out = self._trunk(xin, emb, ctx, W, b, f)
+        return ops.pc_to_cp(out.view(b, f * h * w, self.out_dim), b, self.out_dim, f * h * w).view(b, self.out_dim, f, h, w)
+
+
+class UNetSD_HiGen(_UNetBase):
+    """Drop-in for tools/modules/unet/unet_higen.py:175-176 (MODEL 'UNetSD_HiGen'), both stages of
+    inference_higen_entrance.py (:198-203 one-frame spatial stage, :221-229 32-frame temporal stage):
+      * per-frame embeddings = time + motion-similarity + appearance-similarity (:436-443,:387-399);
+      * context = 16 learned tokens cross-attending to the projected text (:154-172);
+      * the spatial prior enters through img_embedding right after the first conv (:544-547);
+      * every temporal branch is multiplied by 0 when f == 1 (:80-83,:146-149) -- skipped here."""
+    KIND = "higen"
+    WOIMG = True
+
+    def _context_tokens(self, y16, W, b):
+        """TextContextCrossTransformerMultiLayer.forward (unet_higen.py:167-172) -> [b, num_tokens, context_dim]."""
+        p = "context_embedding."
+        E, T = self.embed_dim, self.num_tokens
+        yy = ops.linear(y16.view(-1, y16.shape[-1]), W[p + "input_mapping.w"], bias=W[p + "input_mapping.b"]).view(b, -1, E)
+        tok = torch.empty(b, T, E, device=y16.device, dtype=torch.float16)
+        for bi in range(b):
+            ops.copy2d(W[p + "tokens"], tok[bi])
+        tok = tok.view(b * T, E)
+        heads = 8
+        for d in range(self.plan.context_embedding_depth):
+            q = f"{p}context_transformer.{d}."
+            for att, nrm in (("attn1.", "norm1."), ("attn2.", "norm2.")):
+                xn = ops.layer_norm(tok, W[q + nrm + "g"], W[q + nrm + "b"])
+                qq = ops.linear(xn, W[q + att + "q"]).view(b, T, E)
+                kv = ops.linear(yy.view(-1, E), W[q + att + "kv"]).view(b, -1, 2 * E)
+                a = ops.attention_cross_small(qq, kv[:, :, :E], kv[:, :, E:], heads)
+                tok = ops.linear(a.view(-1, E), W[q + att + "to_out.0.w"], bias=W[q + att + "to_out.0.b"], residual=tok)
+            tok = self._feed_forward(tok, W, q)
+        out = ops.linear(tok, W[p + "output_mapping.w"], bias=W[p + "output_mapping.b"])
+        return out.view(b, T, self.context_dim)
+
+    def _frame_embeddings(self, t, fps, motion_cond, appearance_cond, W, b, f):
+        """[b*f, embed_dim]: time (+fps) embedding of the video repeated per frame + motion + appearance."""
+        tt = t.reshape(-1).repeat_interleave(f)                   # index plumbing; the MLP is row-wise
+        emb = self._time_embedding(tt, None if fps is None else fps.reshape(-1).repeat_interleave(f), W)
+        if f > 1:
+            if motion_cond.size(1) != f:
+                me = ops.sinusoidal_embedding(motion_cond.reshape(-1), self.dim).view(b, f - 1, self.dim)
+                me = ops.interp_linear_rows(me, f)
+            else:
+                me = ops.sinusoidal_embedding(motion_cond.reshape(-1), self.dim)
+            me = self._mlp(me.view(b * f, self.dim), W, "msim_embedding.")
+        else:
+            me = self._mlp(ops.sinusoidal_embedding(motion_cond.reshape(-1), self.dim), W, "msim_embedding.")
+        emb = ops.eltwise("add", emb, me)
+        ac = self._to_f16_rows(appearance_cond.reshape(b, f, -1))
+        return ops.eltwise("add", emb, self._mlp(ac.view(b * f, -1), W, "asim_embedding."))
+
+    @torch.no_grad()
+    def forward(self, x, t, y=None, fps=None, masked=None, video_mask=None, spat_prior=None, motion_cond=None,
+                appearance_cond=None, focus_present_mask=None, prob_focus_present=0., mask_last_frame_num=0, **kwargs):
+        self._check_x(x, t)
+        if y is None or spat_prior is None or motion_cond is None or appearance_cond is None:
+            raise ValueError("UNetSD_HiGen.forward needs y, spat_prior, motion_cond and appearance_cond")
+        W = self._packed or self._pack()
+        b, c, f, h, w = x.shape
+        emb = self._frame_embeddings(t, fps, motion_cond, appearance_cond, W, b, f)
+        ctx = self._context_tokens(self._to_f16_rows(y), W, b)
+        # img_embedding(spat_prior) repeated over the frames, added to the first conv (residual epilogue)
+        sp = ops.cp_to_pc(spat_prior.contiguous().float(), b, spat_prior.shape[1], h * w, c_pad=8).view(b, h, w, 8)
+        img = self._conv3x3_any(sp, W, "img_embedding.").view(b, h * w, self.dim)
+        img_rep = torch.empty(b, f, h * w, self.dim, device=x.device, dtype=torch.float16)
+        for bi in range(b):
+            for fi in range(f):
+                ops.copy2d(img[bi], img_rep[bi, fi])
+        xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=8).view(b * f, h, w, 8)
+        out = self._trunk(xin, emb, ctx, W, b, f, conv_in_residual=img_rep.view(-1, self.dim))
         return ops.pc_to_cp(out.view(b, f * h * w, self.out_dim), b, self.out_dim, f * h * w).view(b, self.out_dim, f, h, w)
