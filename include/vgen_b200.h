@@ -157,6 +157,21 @@ int vgen_scale_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int6
 int vgen_ddim_step(float* xt, const void* y, const void* u, const float* noise, int64_t n, float guide_scale,
                    const float* coef7, int mean_type_v, void* stream);
 
+/* GaussianDiffusion (diffusion_gauss.py), the SR600 sampler pair -- sampler_gauss.cu.
+ * out[b][n_per] = u + guide_scale*(y-u) in fp16 (:206-210) and stats[b][4] = {sum y, sum y^2, sum out, sum out^2}
+ * (fp64, zeroed by the call) for the std-ratio rescale of arXiv:2305.08891 (:212-218). */
+int vgen_cfg_combine(const void* y, const void* u, void* out, int64_t batch, int64_t n_per, float guide_scale,
+                     double* stats, void* stream);
+/* x0 prediction (:220-230) from the fp32 latent xt and the fp16 model output `out`.  stats != NULL applies
+ * out *= guide_rescale*std(y)/std(out) + (1-guide_rescale) first.  pred_type: 0 x0, 1 eps, 2 v;
+ * alpha/sigma are the table entries of the (batch-uniform) timestep. */
+int vgen_gauss_x0(const float* xt, const void* out, const double* stats, float guide_rescale, float alpha, float sigma,
+                  int pred_type, float* x0, int64_t batch, int64_t n_per, void* stream);
+/* out = a0*x0 + a1*x1 + a2*x2 + a3*x3 (fp32; x1..x3 may be NULL; out may alias an input): model-input
+ * scaling (:113), DPM-Solver++(2M) SDE update (:124-139), DDIM inversion step (:408-410) */
+int vgen_lincomb_f32(float* out, int64_t n, const float* x0, float a0, const float* x1, float a1, const float* x2,
+                     float a2, const float* x3, float a3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,8 @@ sampler (sigma schedule, exponential-integrator coefficients, 2M correction) is 
 
 Construction: W is sampled on demand at each queried time by Brownian-bridge interpolation between the
 nearest already-known times (a sorted cache), with a per-time generator seed derived from (entropy,
-time) so that the value at a time does not depend on query order.
+time); the path is reproducible for a given (entropy, query order) -- the reference and the oracle
+query in the same order.
 """
 from __future__ import annotations
 
@@ -20,6 +21,15 @@ import bisect
 import struct
 
 import torch
+
+
+def _mix64(v):
+    """splitmix64 finaliser: torch's CPU generator only consumes the low seed bits, and the IEEE bit
+    patterns of nearby times differ mostly in the high ones."""
+    v &= 0xFFFFFFFFFFFFFFFF
+    v = ((v ^ (v >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    v = ((v ^ (v >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (v ^ (v >> 31)) & 0x7FFFFFFFFFFFFFFF
 
 
 class BrownianTree:
@@ -33,7 +43,7 @@ class BrownianTree:
 
     def _normal(self, t):
         key = struct.unpack("<q", struct.pack("<d", float(t)))[0]
-        g = torch.Generator().manual_seed((self.entropy * 0x9E3779B1 + key) % (2 ** 63 - 1))
+        g = torch.Generator().manual_seed(_mix64(_mix64(self.entropy) ^ key))
         return torch.randn(self.shape, generator=g, dtype=torch.float64)
 
     def _w(self, t):

@@ -84,3 +84,13 @@ def make_inputs(case):
             d["motion_cond"] = torch.tensor([0] * b, dtype=torch.long)
         d["appearance_cond"] = synth.tensor("appearance_cond", (b, f, 32), 0.5, s).abs().clamp(0, 1)
     return d
+
+# SR600 sampler pair (configs/sr600_infer.yaml:41-62, inference_sr600_entrance.py:253-280), shortened ladders
+GAUSS_CASE = dict(
+    unet_case="sr600_tiny",
+    schedules=dict(
+        reverse=dict(schedule="cosine", mean_type="v", schedule_param=dict(num_timesteps=1000, zero_terminal_snr=True)),
+        forward=dict(schedule="logsnr_cosine_interp", mean_type="v",
+                     schedule_param=dict(num_timesteps=1000, zero_terminal_snr=True, scale_min=2.0, scale_max=4.0))),
+    noise_levels=600, reverse_steps=3, steps=4, guide_scale=9.0, guide_rescale=0.3, torch_seed=5,
+)

@@ -146,6 +146,41 @@ def main():
         report[cname] = {"oracle_vs_reference_maxrel": err, "params": int(sum(int(np.prod(s)) for _, s in spec)), **extra}
         print(cname, report[cname], flush=True)
 
+    # ---- GaussianDiffusion / DiffusionDDIMSR (SR600 sampler pair) on the reference, with the torchsde stub
+    from oracle import gauss_oracle as go
+    from oracle.cases import GAUSS_CASE as gc
+    gold = {}
+    for name, kw in gc["schedules"].items():
+        ref_sig = ref.schedules.sigma_schedule(kw["schedule"], **kw["schedule_param"])
+        assert torch.equal(ref_sig, go.sigma_schedule(kw["schedule"], **kw["schedule_param"])), name
+        gold[f"sigmas.{name}"] = ref_sig.numpy()
+    case = CASES[gc["unet_case"]]
+    m = ref.UNetSD_SR600(**case["ctor"]).eval()
+    sd = synth.state_dict(synth.spec_of(m), seed=case["seed"])
+    m.load_state_dict(sd, strict=True)
+    inp = make_inputs(case)
+    from easydict import EasyDict
+    dsr = ref.diffusion_ddim.DiffusionDDIMSR(EasyDict(gc["schedules"]["reverse"]), EasyDict(gc["schedules"]["forward"]))
+    fn = lambda xt, t, **k: vo.unet_sr600_forward(sd, xt, t, **k)  # noqa: E731
+    rev = dsr.reverse_diffusion.ddim_reverse_sample_loop(x0=inp["x"], model=m, model_kwargs={"y": inp["y_neg"]},
+                                                         ddim_timesteps=gc["reverse_steps"], reverse_steps=gc["noise_levels"])
+    o_rev = go.GaussOracle(dsr.reverse_diffusion.sigmas, "v").ddim_reverse_sample_loop(
+        inp["x"], fn, {"y": inp["y_neg"]}, ddim_timesteps=gc["reverse_steps"], reverse_steps=gc["noise_levels"])
+    kw = [{"y": inp["y"]}, {"y": inp["y_neg"]}]
+    skw = dict(guide_scale=gc["guide_scale"], guide_rescale=gc["guide_rescale"], steps=gc["steps"],
+               t_max=gc["noise_levels"] - 1, t_min=0, discretization="trailing")
+    torch.manual_seed(gc["torch_seed"])
+    lat = dsr.forward_diffusion.sample(noise=rev, model=m, model_kwargs=kw, solver="dpmpp_2m_sde", **skw)
+    torch.manual_seed(gc["torch_seed"])
+    o_lat = go.GaussOracle(dsr.forward_diffusion.sigmas, "v").sample_dpmpp_2m_sde(rev, fn, kw, **skw)
+    e_rev, e_lat = _maxrel(o_rev, rev), _maxrel(o_lat, lat)
+    assert e_rev < 2e-5 and e_lat < 1e-4, (e_rev, e_lat)
+    gold["ladder"] = dsr.forward_diffusion._t_to_sigma(torch.arange(gc["noise_levels"] - 1, -1, -(gc["noise_levels"] / (gc["steps"] + 1))).clamp_(0, gc["noise_levels"] - 1)).numpy()
+    gold["reverse_latent"], gold["sample_latent"] = rev.numpy(), lat.numpy()
+    np.savez_compressed(os.path.join(GOLD, "gauss.npz"), **gold)
+    report["gauss"] = {"reverse_err": e_rev, "sample_err": e_lat}
+    print("gauss", report["gauss"], flush=True)
+
     # ---- full-size parameter specs (names/shapes only) for strict state_dict compatibility tests
     from oracle.cases import FULL_CTORS
     for name, (kind, ctor) in FULL_CTORS.items():

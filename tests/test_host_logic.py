@@ -197,3 +197,38 @@ def test_gloo_world2_broadcast_and_sharding(tmp_path):
                         "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout
+
+
+def test_gauss_host_math_is_bit_exact(golden_dir):
+    """GaussianDiffusion host side (sigma tables, ladder, sigma<->t) against the oracle / the reference golden."""
+    from oracle import gauss_oracle as go
+    from oracle.cases import GAUSS_CASE as gc
+    from vgen_b200 import diffusion_gauss as dg
+    g = np.load(os.path.join(golden_dir, "gauss.npz"))
+    d = dg.DiffusionDDIMSR(gc["schedules"]["reverse"], gc["schedules"]["forward"])
+    assert np.array_equal(d.reverse_diffusion.sigmas.numpy(), g["sigmas.reverse"].astype(np.float32))
+    assert np.array_equal(d.forward_diffusion.sigmas.numpy(), g["sigmas.forward"].astype(np.float32))
+    assert d.reverse_diffusion.prediction_type == "v" and d.forward_diffusion.num_timesteps == 1000
+    fwd, o = d.forward_diffusion, go.GaussOracle(torch.from_numpy(g["sigmas.forward"]), "v")
+    for steps, disc in ((4, "trailing"), (30, "trailing"), (7, "linspace"), (5, "leading")):
+        mine = fwd._sigma_ladder(steps, 599, 0, disc, True)
+        ref = o.sample_sigmas(steps, 599, 0, disc, True)
+        assert torch.equal(mine, ref), (steps, disc)
+        for s in mine[:-1]:
+            assert torch.equal(fwd._sigma_to_t(s), o.sigma_to_t(s))
+    assert np.array_equal(fwd._sigma_ladder(4, 599, 0, "trailing", True)[:-1].numpy(), g["ladder"][:4])
+    with pytest.raises(NotImplementedError):
+        fwd.sample(torch.zeros(1, 4, 2, 4, 4), None, solver="heun")
+    M, D, A = vgen_b200.register(force_local=True)
+    assert D.get("DiffusionDDIMSR") is vgen_b200.DiffusionDDIMSR
+
+
+def test_brownian_tree_increments_are_consistent():
+    from vgen_b200.brownian import BrownianTree
+    w0 = torch.zeros(4000)
+    tr = BrownianTree(0.1, w0, 2.1, entropy=7)
+    a, b, c = tr(0.5, 1.0), tr(1.0, 1.7), tr(0.5, 1.7)
+    assert torch.allclose(a + b, c, atol=1e-6)
+    tr2 = BrownianTree(0.1, w0, 2.1, entropy=7)                                 # same seed + same query order -> same path
+    assert torch.equal(tr2(0.5, 1.0), a) and torch.equal(tr2(1.0, 1.7), b)
+    assert abs(float(a.var()) - 0.5) < 0.05 and abs(float(b.var()) - 0.7) < 0.07 and abs(float((a * b).mean())) < 0.05

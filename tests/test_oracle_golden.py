@@ -91,3 +91,30 @@ def test_fourier_filter_is_a_four_bin_update():
                 low = low + (coef * basis).real
         mine = x - (1 - 0.4) * low / (hh * ww)
         assert float((mine - ref).abs().max()) < 1e-5
+
+
+def test_gauss_oracle_matches_reference_golden(golden_dir):
+    """SR600 sampler pair: sigma tables bit-exact, DDIM inversion and DPM-Solver++(2M) SDE latents vs the
+    reference run (same seeded Brownian stub on both sides, oracle/brownian.py)."""
+    from oracle import gauss_oracle as go
+    from oracle.cases import GAUSS_CASE as gc
+    torch.set_grad_enabled(False)
+    g = np.load(os.path.join(golden_dir, "gauss.npz"))
+    sig = {}
+    for name, kw in gc["schedules"].items():
+        sig[name] = go.sigma_schedule(kw["schedule"], **kw["schedule_param"])
+        assert np.array_equal(sig[name].numpy(), g[f"sigmas.{name}"])
+    case, sd, _ = _load(golden_dir, gc["unet_case"])
+    inp = make_inputs(case)
+    fn = lambda xt, t, **k: vo.unet_sr600_forward(sd, xt, t, **k)  # noqa: E731
+    rev = go.GaussOracle(sig["reverse"], "v").ddim_reverse_sample_loop(
+        inp["x"], fn, {"y": inp["y_neg"]}, ddim_timesteps=gc["reverse_steps"], reverse_steps=gc["noise_levels"])
+    assert _maxrel(rev, torch.from_numpy(g["reverse_latent"])) < 5e-5
+    fwd = go.GaussOracle(sig["forward"], "v")
+    lad = fwd.sample_sigmas(gc["steps"], gc["noise_levels"] - 1, 0, "trailing", True)
+    assert np.array_equal(lad[:-1].numpy(), g["ladder"][:gc["steps"]]) and float(lad[-1]) == 0.0
+    torch.manual_seed(gc["torch_seed"])
+    lat = fwd.sample_dpmpp_2m_sde(torch.from_numpy(g["reverse_latent"]), fn, [{"y": inp["y"]}, {"y": inp["y_neg"]}],
+                                  gc["guide_scale"], gc["guide_rescale"], steps=gc["steps"], t_max=gc["noise_levels"] - 1,
+                                  t_min=0, discretization="trailing")
+    assert _maxrel(lat, torch.from_numpy(g["sample_latent"])) < 2e-4

@@ -427,6 +427,31 @@ def group_variants():
         report("scale_copy2d untouched", float(dst[:, :8].abs().max() + dst[:, 48:].abs().max()), 0.0)
     run_case("upsample_rows/scale_copy", f)
 
+    # GaussianDiffusion step kernels (sampler_gauss.cu) vs the reference expressions under fp16 autocast dtypes
+    def f():
+        b, n = 2, 4 * 3 * 10 * 12
+        y, u = rnd(b, 4, 3, 10, 12).half(), rnd(b, 4, 3, 10, 12).half()
+        xt = rnd(b, 4, 3, 10, 12)
+        out, stats = ops.cfg_combine(y, u, 9.0)
+        ref_out = u + 9.0 * (y - u)                                   # fp16 tensor ops, like upstream
+        report("cfg_combine out (bit-exact fp16 op order)", float((out.float() - ref_out.float()).abs().max()), 0.0)
+        s = stats.cpu()
+        for i, (nm, t) in enumerate((("sum y", y), ("sum y^2", y.float() ** 2), ("sum out", ref_out), ("sum out^2", ref_out.float() ** 2))):
+            want = t.double().flatten(1).sum(1).cpu()
+            report(f"cfg_combine stats {nm}", float(((s[:, i] - want).abs() / (want.abs() + 1)).max()), 1e-9)
+        ratio = (y.flatten(1).std(dim=1) / (ref_out.flatten(1).std(dim=1) + 1e-12)).view(-1, 1, 1, 1, 1)
+        resc = ref_out * (0.3 * ratio + (1 - 0.3) * 1.0)
+        al, sg = torch.full((b, 1, 1, 1, 1), 0.8, device="cuda"), torch.full((b, 1, 1, 1, 1), 0.6, device="cuda")  # fp32 tensors, like _i()
+        for pred, want in (("v", al * xt - sg * resc), ("eps", (xt - sg * resc) / al), ("x0", resc.float())):
+            got = ops.gauss_x0(xt, out, 0.8, 0.6, pred, stats, 0.3)
+            report(f"gauss_x0 {pred} with guide_rescale", rel_err(got, want), 2e-3)
+        got = ops.gauss_x0(xt, out, 0.8, 0.6, "v")
+        report("gauss_x0 v no rescale", rel_err(got, al * xt - sg * ref_out), 1e-6)
+        a, c, d = rnd(5, 77), rnd(5, 77), rnd(5, 77)
+        report("lincomb_f32 4 terms", rel_err(ops.lincomb_f32([(0.5, a), (-2.0, c), (3.0, d), (0.25, a)]), 0.75 * a - 2 * c + 3 * d), 1e-6)
+        report("lincomb_f32 1 term in place", rel_err(ops.lincomb_f32([(0.3, a)], out=a.clone()), 0.3 * a), 1e-7)
+    run_case("gauss sampler kernels", f)
+
 
 GROUPS = {
     "variants": group_variants,

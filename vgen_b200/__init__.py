@@ -20,4 +20,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name == "DiffusionDDIM":
         from .diffusion import DiffusionDDIM
         return DiffusionDDIM
+    if name in ("GaussianDiffusion", "DiffusionDDIMSR"):
+        from . import diffusion_gauss
+        return getattr(diffusion_gauss, name)
     raise AttributeError(name)

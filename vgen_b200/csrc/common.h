@@ -34,10 +34,10 @@ int check_cuda(cudaError_t e, const char* what);
     if (!(cond)) return ::vg::fail(std::string(msg) + " [" #cond "]"); \
   } while (0)
 
-// Encode a tiled, 128B-swizzled fp16 tensor map (rank <= 4). dims/box are innermost-first;
-// strides_bytes has rank-1 entries (dims 1..rank-1). Out-of-bounds elements read as zero.
+// Encode a tiled, swizzled (128B default, or 64B) fp16 tensor map (rank <= 4). dims/box are innermost-first;
+// strides_bytes has rank-1 entries (dims 1..rank-1). Out-of-bounds elements read as zero / are not written.
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box);
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 int sm_count();
 extern std::atomic<long long> g_launches;  // kernels launched by this library (vgen_launch_count)

@@ -1,9 +1,18 @@
 // Epilogue shared by the 1-CTA and 2-CTA tap-GEMM kernels: one thread owns one accumulator row (TMEM
 // lane), reads it 32 columns at a time with tcgen05.ld and applies alpha, bias, per-frame bias (ResBlock
 // "h + emb_out"), residual, or GEGLU, rounding to fp16 exactly where the reference materialises an fp16
-// tensor.  Two warps share a TMEM lane quadrant and interleave the 32-column chunks.
-// (A variant that transposed through shared memory for fully coalesced stores was measured 1.4-1.6x SLOWER on
-// the short-K layers - the epilogue is latency-bound, not store-bound - and was removed; see DESIGN.md.)
+// tensor.  Two warps share a TMEM lane quadrant and interleave the 32-column chunks; the four warps that
+// work on the same chunk form a "column group" (128 threads = the 128 rows of the tile).
+//
+// Stores.  A thread-per-row epilogue writes 64 contiguous bytes per thread, i.e. every warp store touches
+// 32 different 128-byte lines: the LSU retires ~16 B/clk/SM, which caps a short-K layer (k=320, n=320)
+// at ~2.9 TB/s of the 6.5 TB/s HBM can deliver.  So the chunk is written to a 64B-swizzled staging tile in
+// shared memory (conflict-free 16-byte stores) and leaves the SM as ONE TMA tile store per (chunk, group):
+// rows x 64 bytes, clipped by the TMA unit at the tensor edges.  Two staging tiles per group ring so the
+// store of chunk i overlaps the math of chunk i+1.  (An earlier variant that re-read the staging tile with
+// ld.shared and issued coalesced st.global from the same warps was 1.4-1.6x slower than direct stores; the
+// TMA store has no second pass through the register file.)  The direct path remains for outputs the TMA
+// cannot address (row stride or base not 16-byte aligned).
 #pragma once
 #include "ptx.cuh"
 #include "tapgemm.h"
@@ -27,12 +36,27 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+static constexpr int kEpiStageBytes = 128 * 64;              // one staging tile: 128 rows x 32 fp16
+static constexpr int kEpiStagingTotal = 4 * kEpiStageBytes;  // 2 column groups x 2 ring slots
+
 struct EpiRow {
   int nb_i;        // n-block index of the tile
   int i3;          // outermost coordinate (frame) of the tile
+  int i1_0, i2_0;  // origin of the tile along d1 / d2 (TMA store coordinates)
   long row;        // output row of this thread (TMEM lane)
   bool row_ok;     // that row is inside the tensor
   uint32_t t_row;  // TMEM address of the thread's lane, column 0 of the accumulator buffer
+};
+
+struct EpiStore {
+  bool tma;                // TMA tile stores (else direct per-thread stores)
+  const CUtensorMap* map;  // output [out_n, d1, d2, d3], box {32, box1, box2, 1}, 64B swizzle
+  uint32_t stage;          // shared address of this column group's two staging tiles
+  uint32_t row_off;        // r * 64: this thread's row inside a staging tile
+  uint32_t row_xor;        // (r >> 1) & 3: 64B-swizzle term of that row
+  int bar_id;              // named barrier of the column group (128 threads)
+  bool leader;             // the one thread of the group that issues / tracks the bulk stores
+  uint32_t slot;           // ring position, carried across chunks and tiles
 };
 
 __device__ __forceinline__ bool tapgemm_vec_ok(const TapGemmEpilogue& e, int out_n) {
@@ -42,21 +66,54 @@ __device__ __forceinline__ bool tapgemm_vec_ok(const TapGemmEpilogue& e, int out
          (e.residual == nullptr || (((e.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0)));
 }
 
+// host side: can the output be written with TMA tile stores?
+inline bool tapgemm_out_tma_ok(const TapGemmEpilogue& e) {
+  return (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (e.ldo & 7) == 0;
+}
+
+// ---- staging-tile protocol of one column group -------------------------------------------------------
+// acquire: the slot written two chunks ago must have been read by its TMA store
+__device__ __forceinline__ void epi_stage_acquire(EpiStore& st) {
+  if (st.leader) bulk_wait_group_read<1>();
+  named_bar_sync(st.bar_id, 128);
+}
+// 16-byte piece j8 (0..3) of this thread's row
+__device__ __forceinline__ void epi_stage_put(const EpiStore& st, int j8, const uint4& o) {
+  const uint32_t addr = st.stage + st.slot * kEpiStageBytes + st.row_off + ((((uint32_t)j8) ^ st.row_xor) << 4);
+  st_shared_v4(addr, o.x, o.y, o.z, o.w);
+}
+// publish: make the generic-proxy writes visible to the TMA unit, then one thread stores the tile
+__device__ __forceinline__ void epi_stage_publish(EpiStore& st, int col, const EpiRow& t) {
+  fence_proxy_async_smem();
+  named_bar_sync(st.bar_id, 128);
+  if (st.leader) {
+    tma_store_4d(st.map, st.stage + st.slot * kEpiStageBytes, col, t.i1_0, t.i2_0, t.i3);
+    bulk_commit_group();
+  }
+  st.slot ^= 1;
+}
+// before the kernel exits every bulk store must have completed
+__device__ __forceinline__ void epi_stage_drain(const EpiStore& st) {
+  if (st.tma && st.leader) bulk_wait_group<0>();
+}
+
 // chunk0 / chunk_step: this warp handles the 32-column chunks chunk0, chunk0 + chunk_step, ... (two warps share
 // a TMEM lane quadrant and split the columns between them).
 __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, const TapGemmEpilogue& e, const EpiRow& t,
-                                                      bool vec_ok, int out_n, int chunk0, int chunk_step) {
+                                                      EpiStore& st, bool vec_ok, int out_n, int chunk0, int chunk_step) {
   const int BN = s.bn;
   if (!e.geglu) {
     const int n0 = t.nb_i * BN;
     __half* orow = e.out + t.row * e.ldo;
     const __half* rrow = e.residual ? e.residual + t.row * e.ldr : nullptr;
-    const __half* grow = e.group_bias ? e.group_bias + (long)(t.i3 / e.group_bias_div) * e.ld_group_bias : nullptr;
+    const __half* grow = e.group_bias ? e.group_bias + (long)fd_div(e.f_group_bias_div, t.i3) * e.ld_group_bias : nullptr;
     for (int c0 = chunk0 * 32; c0 < BN; c0 += chunk_step * 32) {
+      const int nbase = n0 + c0;
+      if (nbase >= s.n) break;  // uniform over the column group
       uint32_t v[32];
       tmem_ld32(t.t_row + c0, v);
-      const int nbase = n0 + c0;
-      const bool fast = vec_ok && t.row_ok && nbase + 32 <= s.n;
+      const bool full = nbase + 32 <= s.n;
+      const bool fast = vec_ok && t.row_ok && full;
       // issue the (HBM / L2 latency) residual and per-frame-bias loads before blocking on the TMEM load
       uint4 r4[4], g4[4];
       if (fast) {
@@ -66,9 +123,9 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
           if (grow) g4[j8] = __ldg(reinterpret_cast<const uint4*>(grow + nbase + j8 * 8));
         }
       }
+      const bool staged = st.tma && vec_ok && full;  // uniform over the column group
+      if (staged) epi_stage_acquire(st);
       tmem_ld_wait();
-      if (!t.row_ok) continue;
-      if (nbase >= s.n) continue;
       if (fast) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
@@ -97,9 +154,10 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
           o.y = pack_half2(f[2], f[3]);
           o.z = pack_half2(f[4], f[5]);
           o.w = pack_half2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(orow + nbase + j8 * 8) = o;
+          if (staged) epi_stage_put(st, j8, o);
+          else *reinterpret_cast<uint4*>(orow + nbase + j8 * 8) = o;
         }
-      } else {
+      } else if (t.row_ok) {
         for (int j = 0; j < 32; ++j) {
           const int n = nbase + j;
           if (n >= s.n) break;
@@ -110,6 +168,7 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
           orow[n] = __float2half_rn(a);
         }
       }
+      if (staged) epi_stage_publish(st, nbase, t);  // rows outside the tensor are clipped by the TMA unit
     }
   } else {
     // GEGLU: columns [0,BN/2) of this tile are "value" j, columns [BN/2,BN) the matching "gate" j
@@ -118,48 +177,54 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
     const int o0 = t.nb_i * hb;
     __half* orow = e.out + t.row * e.ldo;
     for (int c0 = chunk0 * 32; c0 < hb; c0 += chunk_step * 32) {
+      const int obase = o0 + c0;
+      if (obase >= out_n) break;  // uniform over the column group
       uint32_t v[32], g[32];
       tmem_ld32(t.t_row + c0, v);
       tmem_ld32(t.t_row + hb + c0, g);
+      const bool full = obase + 32 <= out_n;
+      const bool staged = st.tma && vec_ok && full;
+      if (staged) epi_stage_acquire(st);
       tmem_ld_wait();
-      if (!t.row_ok) continue;
-      const int obase = o0 + c0;
-      if (obase >= out_n) continue;
-      const int wbase = t.nb_i * BN + c0;  // packed weight-row index of value j (gate is + hb)
-      float f[32];
+      if (t.row_ok) {
+        const int wbase = t.nb_i * BN + c0;  // packed weight-row index of value j (gate is + hb)
+        float f[32];
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-        if (e.bias) {  // packed bias is 16-byte aligned and wbase is a multiple of 32
-          bv = __ldg(reinterpret_cast<const float4*>(e.bias + wbase + j4 * 4));
-          bg = __ldg(reinterpret_cast<const float4*>(e.bias + wbase + hb + j4 * 4));
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+          if (e.bias) {  // packed bias is 16-byte aligned and wbase is a multiple of 32
+            bv = __ldg(reinterpret_cast<const float4*>(e.bias + wbase + j4 * 4));
+            bg = __ldg(reinterpret_cast<const float4*>(e.bias + wbase + hb + j4 * 4));
+          }
+          const float bva[4] = {bv.x, bv.y, bv.z, bv.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 * 4 + jj;
+            const float a = fmaf(__uint_as_float(v[j]), e.alpha, bva[jj]);
+            const float b = fmaf(__uint_as_float(g[j]), e.alpha, bga[jj]);
+            // reference rounds the projection to fp16, gelu to fp16, product to fp16
+            const float a16 = __half2float(__float2half_rn(a));
+            const float b16 = __half2float(__float2half_rn(b));
+            const float ge = __half2float(__float2half_rn(gelu_erf(b16)));
+            f[j] = a16 * ge;
+          }
         }
-        const float bva[4] = {bv.x, bv.y, bv.z, bv.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+        if (vec_ok && full) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = j4 * 4 + jj;
-          const float a = fmaf(__uint_as_float(v[j]), e.alpha, bva[jj]);
-          const float b = fmaf(__uint_as_float(g[j]), e.alpha, bga[jj]);
-          // reference rounds the projection to fp16, gelu to fp16, product to fp16
-          const float a16 = __half2float(__float2half_rn(a));
-          const float b16 = __half2float(__float2half_rn(b));
-          const float ge = __half2float(__float2half_rn(gelu_erf(b16)));
-          f[j] = a16 * ge;
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 o;
+            o.x = pack_half2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+            o.y = pack_half2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+            o.z = pack_half2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+            o.w = pack_half2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+            if (staged) epi_stage_put(st, j8, o);
+            else *reinterpret_cast<uint4*>(orow + obase + j8 * 8) = o;
+          }
+        } else {
+          for (int j = 0; j < 32 && obase + j < out_n; ++j) orow[obase + j] = __float2half_rn(f[j]);
         }
       }
-      if (vec_ok && obase + 32 <= out_n) {
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          uint4 o;
-          o.x = pack_half2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-          o.y = pack_half2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-          o.z = pack_half2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-          o.w = pack_half2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-          *reinterpret_cast<uint4*>(orow + obase + j8 * 8) = o;
-        }
-      } else {
-        for (int j = 0; j < 32 && obase + j < out_n; ++j) orow[obase + j] = __float2half_rn(f[j]);
-      }
+      if (staged) epi_stage_publish(st, obase, t);
     }
   }
 }

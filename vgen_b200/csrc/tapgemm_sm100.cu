@@ -37,6 +37,8 @@ static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
 struct alignas(64) TapGemmKernelParams {
   CUtensorMap map_a;
   CUtensorMap map_b;
+  CUtensorMap map_out;  // output, box {32, box1, box2, 1}, 64B swizzle (TMA tile stores of the epilogue)
+  int out_tma;          // 1: map_out is valid
   TapGemmShape s;
   TapGemmEpilogue e;
   int stages;
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
   const int stage_bytes = kABytes + p.b_slot_bytes;
 
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)stages * stage_bytes;   // epilogue staging tiles (1024-aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiStagingTotal);
   uint64_t* full_bar = bars;                 // [stages]
   uint64_t* empty_bar = bars + stages;       // [stages]
   uint64_t* tfull_bar = bars + 2 * stages;   // [2]
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
+    if (p.out_tma) tma_prefetch_desc(&p.map_out);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -91,30 +95,30 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // the whole warp walks the loop (warp-uniform operands); one elected lane issues the TMA
-    uint32_t it_g = 0;
+    int st = 0;
+    uint32_t ph = 0;  // ring position / phase, carried across tiles
     for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x) {
-      int nb_i = tile % s.nb;
-      int rest = tile / s.nb;
-      const int t1_i = rest % s.t1;
-      rest /= s.t1;
-      const int t2_i = rest % s.t2;
-      const int i3 = rest / s.t2;
+      int m, nb_i, rest, t1_i, i3, t2_i;
+      fd_divmod(s.f_nb, tile, m, nb_i);
+      fd_divmod(s.f_t1, m, rest, t1_i);
+      fd_divmod(s.f_t2, rest, i3, t2_i);
       const int i1_0 = t1_i * s.box1, i2_0 = t2_i * s.box2, n0 = nb_i * BN;
-      int tap = 0, kc_i = 0;
-      for (int it = 0; it < k_iters; ++it, ++it_g) {
-        const int st = it_g % stages;
-        const uint32_t ph = (it_g / stages) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1, 1);
-        if (elect_one()) {
-          mbar_expect_tx(&full_bar[st], stage_tx);
-          uint8_t* sa = tiles + (size_t)st * stage_bytes;
-          tma_load_4d(sa, &p.map_a, &full_bar[st], kc_i * kBK, i1_0 + s.tap1[tap], i2_0 + s.tap2[tap], i3 + s.tap3[tap]);
-          tma_load_2d(sa + kABytes, &p.map_b, &full_bar[st], tap * s.c + kc_i * kBK, n0);
-        }
-        __syncwarp();
-        if (++kc_i == s.kc) {
-          kc_i = 0;
-          ++tap;
+      for (int tap = 0; tap < s.num_taps; ++tap) {
+        const int c1 = i1_0 + s.tap1[tap], c2 = i2_0 + s.tap2[tap], c3 = i3 + s.tap3[tap];
+        const int wk0 = tap * s.c;
+        for (int kc_i = 0; kc_i < s.kc; ++kc_i) {
+          mbar_wait(&empty_bar[st], ph ^ 1, 1);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[st], stage_tx);
+            uint8_t* sa = tiles + (size_t)st * stage_bytes;
+            tma_load_4d(sa, &p.map_a, &full_bar[st], kc_i * kBK, c1, c2, c3);
+            tma_load_2d(sa + kABytes, &p.map_b, &full_bar[st], wk0 + kc_i * kBK, n0);
+          }
+          __syncwarp();
+          if (++st == stages) {
+            st = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -123,16 +127,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
     // whole warp in the loop, one elected lane issues tcgen05.mma / commit
     const uint32_t idesc = umma_idesc_f16(kBM, BN, 0, 0);
     const uint32_t tiles_addr = smem_u32(tiles);
-    uint32_t it_g = 0;
+    int st = 0;
+    uint32_t ph = 0;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
       mbar_wait(&tempty_bar[as], aph ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * 256;
-      for (int it = 0; it < k_iters; ++it, ++it_g) {
-        const int st = it_g % stages;
-        const uint32_t ph = (it_g / stages) & 1;
+      for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full_bar[st], ph, 3);
         tc_fence_after();
         if (elect_one()) {
@@ -148,6 +151,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
           if (it == k_iters - 1) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
+        if (++st == stages) {
+          st = 0;
+          ph ^= 1;
+        }
       }
     }
   } else {
@@ -158,18 +165,30 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
     const int rows_in_tile = s.box1 * s.box2;
     const int out_n = e.geglu ? (s.n >> 1) : s.n;
     const bool vec_ok = tapgemm_vec_ok(e, out_n);
+    int r1, r2;                       // position of this thread's row inside the box (tile-invariant)
+    fd_divmod(s.f_box1, r, r2, r1);
+    const int cg = (warp - 2) >> 2;   // column group: the 4 warps (all lane quadrants) working on the same chunk
+    EpiStore est;
+    est.tma = p.out_tma != 0;
+    est.map = &p.map_out;
+    est.stage = smem_u32(staging) + (uint32_t)cg * 2u * kEpiStageBytes;
+    est.row_off = (uint32_t)r * 64u;
+    est.row_xor = ((uint32_t)r >> 1) & 3u;
+    est.bar_id = 1 + cg;
+    est.leader = (r == 0);
+    est.slot = 0;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
       EpiRow t;
-      t.nb_i = tile % s.nb;
-      int rest = tile / s.nb;
-      const int t1_i = rest % s.t1;
-      rest /= s.t1;
-      const int t2_i = rest % s.t2;
-      t.i3 = rest / s.t2;
-      const int i1 = t1_i * s.box1 + (r % s.box1);
-      const int i2 = t2_i * s.box2 + (r / s.box1);
+      int m, rest, t1_i, t2_i;
+      fd_divmod(s.f_nb, tile, m, t.nb_i);
+      fd_divmod(s.f_t1, m, rest, t1_i);
+      fd_divmod(s.f_t2, rest, t.i3, t2_i);
+      t.i1_0 = t1_i * s.box1;
+      t.i2_0 = t2_i * s.box2;
+      const int i1 = t.i1_0 + r1;
+      const int i2 = t.i2_0 + r2;
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
       t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
 
@@ -182,12 +201,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, vec_ok, out_n, (warp - 2) >> 2, 2);
+      tapgemm_epilogue_tile(s, e, t, est, vec_ok, out_n, cg, 2);
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(&tempty_bar[as]);
     }
+    epi_stage_drain(est);
   }
 
   tc_fence_before();
@@ -212,7 +232,9 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
 
   TapGemmKernelParams p;
   p.s = s;
+  tapgemm_prepare_shape(p.s);
   p.e = a.epi;
+  p.e.f_group_bias_div = make_fastdiv(p.e.group_bias_div > 1 ? p.e.group_bias_div : 1);
   {
     const uint64_t dims[4] = {(uint64_t)s.c, (uint64_t)s.d1, (uint64_t)s.d2, (uint64_t)s.d3};
     const uint64_t strides[3] = {(uint64_t)a.a_stride1 * 2, (uint64_t)a.a_stride2 * 2, (uint64_t)a.a_stride3 * 2};
@@ -229,12 +251,24 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
   }
   p.b_slot_bytes = ((s.bn * kBK * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes + p.b_slot_bytes;
-  const int budget = 224 * 1024;
+  const int budget = 224 * 1024 - kEpiStagingTotal;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + kEpiStagingTotal + (2 * stages + 6) * 8 + 1024;
+  {
+    const int out_n = a.epi.geglu ? s.n / 2 : s.n;
+    p.out_tma = (tapgemm_out_tma_ok(a.epi) && out_n >= 32 && !getenv("VGEN_TAPGEMM_DIRECT_STORE")) ? 1 : 0;
+    if (p.out_tma) {
+      const uint64_t ld = (uint64_t)a.epi.ldo * 2;
+      const uint64_t dims[4] = {(uint64_t)out_n, (uint64_t)s.d1, (uint64_t)s.d2, (uint64_t)s.d3};
+      const uint64_t strides[3] = {ld, ld * s.d1, ld * s.d1 * s.d2};
+      const uint32_t box[4] = {32, (uint32_t)s.box1, (uint32_t)s.box2, 1};
+      int rc = make_tmap_f16(&p.map_out, a.epi.out, 4, dims, strides, box, 64);
+      if (rc) return rc;
+    }
+  }
 
   static bool attr_done = false;
   if (!attr_done) {

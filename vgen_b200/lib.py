@@ -68,6 +68,9 @@ _SIGNATURES = {
     "vgen_adaptive_avgpool": [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp],
     "vgen_vae_sample": [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp],
     "vgen_ddim_step": [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _i32, _vp],
+    "vgen_cfg_combine": [_vp, _vp, _vp, _i64, _i64, _f32, _vp, _vp],
+    "vgen_gauss_x0": [_vp, _vp, _vp, _f32, _f32, _f32, _i32, _vp, _i64, _i64, _vp],
+    "vgen_lincomb_f32": [_vp, _i64, _vp, _f32, _vp, _f32, _vp, _f32, _vp, _f32, _vp],
 }
 _RESTYPES = {"vgen_last_error": ctypes.c_char_p, "vgen_launch_count": ctypes.c_int64,
              "vgen_group_norm_workspace_bytes": ctypes.c_int64}

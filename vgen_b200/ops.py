@@ -484,6 +484,51 @@ def ddim_step_(xt, y, u, coef7, guide_scale, mean_type_v=True, noise=None):
     return xt
 
 
+def cfg_combine(y, u, guide_scale):
+    """out = u + g*(y-u) (fp16) and the fp64 per-sample sums needed by the std-ratio guidance rescale."""
+    _chk16(y, "y"), _chk16(u, "u")
+    if y.shape != u.shape or not y.is_contiguous() or not u.is_contiguous():
+        raise _l.VgenError("cfg_combine: y/u must be contiguous and equally shaped")
+    b = y.shape[0]
+    out = torch.empty_like(y)
+    stats = torch.empty(b, 4, device=y.device, dtype=torch.float64)
+    rc = _l.load().vgen_cfg_combine(_p(y), _p(u), _p(out), b, y.numel() // b, float(guide_scale), _p(stats), _stream())
+    _l.check(rc, "vgen_cfg_combine")
+    return out, stats
+
+
+def gauss_x0(xt, out, alpha, sigma, prediction_type, stats=None, guide_rescale=0.0):
+    """x0 prediction of GaussianDiffusion.denoise from the fp32 latent and the fp16 model output."""
+    _chk16(out, "out")
+    if xt.dtype != torch.float32 or not xt.is_contiguous() or not out.is_contiguous() or xt.shape != out.shape:
+        raise _l.VgenError("gauss_x0: xt must be contiguous fp32 and shaped like out")
+    b = xt.shape[0]
+    x0 = torch.empty_like(xt)
+    rc = _l.load().vgen_gauss_x0(_p(xt), _p(out), _p(stats), float(guide_rescale), float(alpha), float(sigma),
+                                 {"x0": 0, "eps": 1, "v": 2}[prediction_type], _p(x0), b, xt.numel() // b, _stream())
+    _l.check(rc, "vgen_gauss_x0")
+    return x0
+
+
+def lincomb_f32(terms, out=None):
+    """out = sum_i a_i * x_i over up to four (a_i, x_i) fp32 terms."""
+    if not 1 <= len(terms) <= 4:
+        raise _l.VgenError("lincomb_f32: 1..4 terms")
+    x0 = terms[0][1]
+    for a, x in terms:
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.shape != x0.shape or not x.is_cuda:
+            raise _l.VgenError("lincomb_f32: terms must be contiguous CUDA fp32 tensors of one shape")
+    if out is None:
+        out = torch.empty_like(x0)
+    args = []
+    for i in range(4):
+        a, x = terms[i] if i < len(terms) else (0.0, None)
+        args += [_p(x), float(a)]
+    rc = _l.load().vgen_lincomb_f32(_p(out), x0.numel(), *args, _stream())
+    _l.check(rc, "vgen_lincomb_f32")
+    return out
+
+
 def vae_sample(moments, noise, scale):
     """moments fp16 [n, p, 2*zc] (mean | logvar), noise fp32 [n, zc, p] -> fp32 z [n, zc, p]."""
     _chk16(moments, "moments")

@@ -62,6 +62,7 @@ def register(force_local: bool = False):
     global MODEL, DIFFUSION, AUTO_ENCODER, USING_REFERENCE_REGISTRY
     from .autoencoder import AutoencoderKL
     from .diffusion import DiffusionDDIM
+    from .diffusion_gauss import DiffusionDDIMSR
     from .unet import UNetSD_HiGen, UNetSD_I2VGen, UNetSD_SR600, UNetSD_T2VBase, UNetSD_VideoLCM
 
     regs = None
@@ -81,5 +82,6 @@ def register(force_local: bool = False):
         for cls in (UNetSD_T2VBase, UNetSD_I2VGen, UNetSD_VideoLCM, UNetSD_SR600, UNetSD_HiGen):
             MODEL.register_class()(cls)
         DIFFUSION.register_class()(DiffusionDDIM)
+        DIFFUSION.register_class()(DiffusionDDIMSR)
         AUTO_ENCODER.register_class()(AutoencoderKL)
     return MODEL, DIFFUSION, AUTO_ENCODER
