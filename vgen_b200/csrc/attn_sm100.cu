@@ -9,10 +9,13 @@
 //
 // One CTA = 256 query rows (two 128-row tiles) of one (batch, head), 10 warps:
 //   warps 0-3 / 4-7  softmax + output for q-tile 0 / 1 (thread r <-> TMEM lane r)
-//   warp 8           TMA producer: Q once, then a 3-stage ring of (K,V) blocks of 128 keys
+//   warp 8           TMA producer: Q once, then separate 2-slot rings of K and V blocks of 128 keys (K(j) is
+//                    released as soon as both tiles' QK(j) ran, long before V(j))
 //   warp 9           tcgen05.mma issue (whole warp walks the loop, one elected lane issues)
 // The two q-tiles ping-pong on the tensor pipe: while the softmax warps of tile 0 work on S0(j+1), the
-// tensor core runs PV1(j) and QK1(j+1).
+// tensor core runs PV1(j) and QK1(j+1).  P is double-buffered per tile, so the exponentials of block j never
+// wait for PV(j-1) (that wait was 23% of the softmax warps' time with a single P buffer: the PV round trip
+// -- poll, issue, 256 tensor cycles, commit, wake-up -- is ~900 cycles); only the rare O rescale does.
 //
 // Per key block and tile the softmax thread reads its 128 scores from TMEM ONCE (four tcgen05.ld in flight,
 // one wait), takes the row max, and exponentiates against a reference max m_ref that is only advanced when
@@ -32,7 +35,7 @@ static constexpr int kTileK = 128;   // keys per block (UMMA N of QK^T)
 static constexpr int kQBytes = kTileQ * kD * 2;   // 16 KB
 static constexpr int kKBytes = kTileK * kD * 2;   // 16 KB
 static constexpr int kPBytes = kTileQ * kTileK * 2;  // 32 KB per q-tile
-static constexpr int kKvStages = 3;   // (K,V) ring: block j+2 is in flight while block j is being consumed
+static constexpr int kKvStages = 2;   // K ring and V ring, 2 slots each
 static constexpr float kRescaleThreshold = 8.0f;     // log2 units: P <= 2^8
 
 struct alignas(64) AttnParams {
@@ -51,17 +54,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 2 x 16 KB
-  uint8_t* sKV = sQ + 2 * kQBytes;                     // stages x (K 16 KB + V 16 KB)
-  uint8_t* sP = sKV + kKvStages * 2 * kKBytes;         // 2 x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint8_t* sK = sQ + 2 * kQBytes;                      // 2 x 16 KB
+  uint8_t* sV = sK + kKvStages * kKBytes;              // 2 x 16 KB
+  uint8_t* sP = sV + kKvStages * kKBytes;              // 2 tiles x 2 buffers x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kPBytes);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [kKvStages <= 4]
-  uint64_t* kv_empty = bars + 5;      // [kKvStages <= 4]
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2] both tiles' QK(j) finished
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2] both tiles' PV(j) finished
   uint64_t* s_full = bars + 9;        // [2] per q-tile: S(j) written by QK
-  uint64_t* p_full = bars + 11;       // [2] per q-tile: P(j) in smem, S(j) consumed, O rescaled
-  uint64_t* o_full = bars + 13;       // [2] per q-tile: PV(j) finished (P buffer free, O readable)
-  uint64_t* s_free = bars + 15;       // [2] per q-tile: S(j) is in registers, QK(j+1) may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* p_full = bars + 11;       // [2][2] per q-tile and P buffer: P(j) in smem, S(j) consumed, O rescaled
+  uint64_t* o_full = bars + 15;       // [2][2] per q-tile and P buffer: PV(j) finished (buffer j&1 free, O readable)
+  uint64_t* s_free = bars + 19;       // [2] per q-tile: S(j) is in registers, QK(j+1) may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  // (one barrier per P buffer: the softmax warps may publish P(j+1) before the MMA warp has looked at P(j), and a
+  // single barrier two phases ahead of its observer aliases)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
@@ -74,13 +82,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
     tma_prefetch_desc(&p.map_v);
     mbar_init(q_full, 1);
     for (int i = 0; i < kKvStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&o_full[i], 1);
+      mbar_init(&p_full[2 * i], 4);
+      mbar_init(&p_full[2 * i + 1], 4);
+      mbar_init(&o_full[2 * i], 1);
+      mbar_init(&o_full[2 * i + 1], 1);
       mbar_init(&s_free[i], 4);
     }
     fence_mbar_init();
@@ -104,30 +116,49 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       tma_load_4d(sQ + kQBytes, &p.map_q, q_full, 0, head, q0 + kTileQ, batch);
     }
     __syncwarp();
-    for (int j = 0; j < nkv; ++j) {
-      const int st = j % kKvStages;
-      const uint32_t ph = (j / kKvStages) & 1;
-      mbar_wait(&kv_empty[st], ph ^ 1, 10);
-      if (elect_one()) {
-        mbar_expect_tx(&kv_full[st], 2 * kKBytes);
-        uint8_t* dst = sKV + st * 2 * kKBytes;
-        tma_load_4d(dst, &p.map_k, &kv_full[st], 0, head, j * kTileK, kvb);
-        tma_load_4d(dst + kKBytes, &p.map_v, &kv_full[st], 0, head, j * kTileK, kvb);
+    // K and V rings are filled independently, whichever slot frees first (use u of slot s is block 2u + s)
+    int k_next = 0, v_next = 0;
+    long long t_idle = 0;
+    while (k_next < nkv || v_next < nkv) {
+      bool progressed = false;
+      if (k_next < nkv && (k_next < kKvStages || mbar_test_wait(&k_empty[k_next & 1], ((k_next >> 1) - 1) & 1))) {
+        if (elect_one()) {
+          mbar_expect_tx(&k_full[k_next & 1], kKBytes);
+          tma_load_4d(sK + (k_next & 1) * kKBytes, &p.map_k, &k_full[k_next & 1], 0, head, k_next * kTileK, kvb);
+        }
+        __syncwarp();
+        ++k_next;
+        progressed = true;
       }
-      __syncwarp();
+      if (v_next < nkv && (v_next < kKvStages || mbar_test_wait(&v_empty[v_next & 1], ((v_next >> 1) - 1) & 1))) {
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[v_next & 1], kKBytes);
+          tma_load_4d(sV + (v_next & 1) * kKBytes, &p.map_v, &v_full[v_next & 1], 0, head, v_next * kTileK, kvb);
+        }
+        __syncwarp();
+        ++v_next;
+        progressed = true;
+      }
+      if (progressed) {
+        t_idle = 0;
+      } else {
+        if (t_idle == 0) t_idle = clock64();
+        else if (clock64() - t_idle > VG_WATCHDOG_CYCLES) mbar_deadlock(10, 0);
+      }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issue (warp-uniform loop)
     const uint32_t idesc_qk = umma_idesc_f16(kTileQ, kTileK, 0, 0);
     const uint32_t idesc_pv = umma_idesc_f16(kTileQ, kD, 0, 1);  // B (= V) is MN-major
-    const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV), p_addr0 = smem_u32(sP);
-    auto issue_qk = [&](int i, int j) {
+    const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr0 = smem_u32(sV), p_addr0 = smem_u32(sP);
+    auto issue_qk = [&](int i, int j, bool release_k) {
       if (elect_one()) {
         const uint64_t a_desc = umma_desc_sw128(q_addr + i * kQBytes, 16, 1024);
-        const uint64_t b_desc = umma_desc_sw128(kv_addr + (j % kKvStages) * 2 * kKBytes, 16, 1024);
+        const uint64_t b_desc = umma_desc_sw128(k_addr + (j & 1) * kKBytes, 16, 1024);
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) umma_f16_ss(tmem + i * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[i]);
+        if (release_k) umma_commit(&k_empty[j & 1]);  // K(j) consumed by both tiles
       }
       __syncwarp();
     };
@@ -135,9 +166,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
     // registers (s_free), i.e. it overlaps their exponentials; PV_i(j) goes out when P_i(j) is in shared memory.
     auto issue_pv = [&](int i, int j, bool release_kv) {
       if (elect_one()) {
-        const int st = j % kKvStages;
-        const uint32_t v_addr = kv_addr + st * 2 * kKBytes + kKBytes;
-        const uint32_t p_addr = p_addr0 + i * kPBytes;
+        const int st = j & 1;
+        const uint32_t v_addr = v_addr0 + st * kKBytes;
+        const uint32_t p_addr = p_addr0 + (2 * i + (j & 1)) * kPBytes;
 #pragma unroll
         for (int ks = 0; ks < kTileK / 16; ++ks) {
           // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
@@ -146,8 +177,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
           const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
           umma_f16_ss(tmem + 256 + i * 64, a_desc, b_desc, idesc_pv, (j | ks) != 0);  // O accumulates over blocks
         }
-        umma_commit(&o_full[i]);
-        if (release_kv) umma_commit(&kv_empty[st]);  // K(j), V(j) fully consumed by both tiles
+        umma_commit(&o_full[2 * i + (j & 1)]);
+        if (release_kv) umma_commit(&v_empty[st]);  // V(j) consumed by both tiles
       }
       __syncwarp();
     };
@@ -160,14 +191,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       for (int i = 0; i < 2; ++i) {
         const int jq = qk_next[i];
         if (jq < nkv && (jq == 0 || mbar_test_wait(&s_free[i], (jq - 1) & 1)) &&
-            mbar_test_wait(&kv_full[jq % kKvStages], (jq / kKvStages) & 1)) {
+            mbar_test_wait(&k_full[jq & 1], (jq >> 1) & 1)) {
           tc_fence_after();
-          issue_qk(i, jq);
+          issue_qk(i, jq, qk_next[1 - i] > jq);
           qk_next[i] = jq + 1;
           progressed = true;
         }
         const int jp = pv_next[i];
-        if (jp < nkv && mbar_test_wait(&p_full[i], jp & 1)) {
+        if (jp < nkv && mbar_test_wait(&p_full[2 * i + (jp & 1)], (jp >> 1) & 1) &&
+            mbar_test_wait(&v_full[jp & 1], (jp >> 1) & 1)) {
           tc_fence_after();
           issue_pv(i, jp, pv_next[1 - i] > jp);
           pv_next[i] = jp + 1;
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t t_s = tmem + i * 128 + lane_base;
     const uint32_t t_o = tmem + 256 + i * 64 + lane_base;
-    const uint32_t prow = smem_u32(sP + i * kPBytes + r * 128);
+    const uint32_t prow0 = smem_u32(sP + 2 * i * kPBytes + r * 128);
     const int sw = r & 7;
     const float sl2 = p.scale_log2;
 
@@ -225,17 +257,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       }
       const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
-      // P(j-1) consumed and O(j-1) complete before P(j) is written / O is touched
-      if (j > 0) {
-        mbar_wait(&o_full[i], (j - 1) & 1, 21);
-        tc_fence_after();
-      }
       // advance the reference max only when the true max has outgrown it by more than the threshold
       const bool grow = (m_blk - m_ref) * sl2 > kRescaleThreshold;   // always true on the first block
       if (__any_sync(0xffffffffu, grow)) {
         const float m_new = grow ? m_blk : m_ref;
         const float alpha = (j == 0) ? 0.f : fast_exp2((m_ref - m_new) * sl2);  // 1 for rows that do not advance
         if (j > 0) {
+          // O must be complete up to PV(j-1) before it is touched (the (j-1)/2-th use of that P buffer's barrier)
+          mbar_wait(&o_full[2 * i + ((j - 1) & 1)], ((j - 1) >> 1) & 1, 21);
+          tc_fence_after();
           // rescale this row of O in TMEM; the score registers are dead here and reloaded afterwards
           uint32_t o[32];
 #pragma unroll 1
@@ -269,6 +299,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[i]);
+      // P buffer j&1 was last read by PV(j-2)
+      if (j >= 2) mbar_wait(&o_full[2 * i + (j & 1)], ((j >> 1) - 1) & 1, 23);
+      const uint32_t prow = prow0 + (j & 1) * kPBytes;
       const float neg_ms = -m_ref * sl2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       // p = exp2(s*scale*log2e - m_ref*scale*log2e), row sum, P -> smem (128B-swizzled K-major UMMA layout)
@@ -296,10 +329,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
+      if (lane == 0) mbar_arrive(&p_full[2 * i + (j & 1)]);
     }
     // ---- output: O / l
-    mbar_wait(&o_full[i], (nkv - 1) & 1, 22);
+    mbar_wait(&o_full[2 * i + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1, 22);
     tc_fence_after();
     const int row = q0 + i * kTileQ + r;
     const float inv_l = 1.0f / l_run;
@@ -378,7 +411,7 @@ extern "C" int vgen_attention_d64(const void* q, const void* k, const void* v, v
   p.heads = (int)heads;
   p.kv_batch_div = (int)kv_batch_div;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 2 * kPBytes + 18 * 8 + 16 + 1024;
+  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 22 * 8 + 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
