@@ -8,7 +8,7 @@
 
 namespace vg {
 
-__device__ __forceinline__ float silu_e(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_e(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // ------------------------------------------------------------------ layout: [n][c][p] <-> [n][p][c]
 // boundary of MODEL.forward: x arrives as fp32 [b, c, f, h, w] (reference layout, unet_t2v.py:257) and

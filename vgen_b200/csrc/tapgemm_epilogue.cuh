@@ -20,20 +20,27 @@
 namespace vg {
 
 // exact-erf GELU (F.gelu default, util.py:714) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below
-// the fp16 rounding the result receives): 2 MUFU + ~14 FMA-pipe instructions instead of libm erff's ~30.
+// the fp16 rounding the result receives).  Written so that no cancellation and no sign fix-up is needed:
+//   c = 1 - erf(|x|/sqrt2) = poly(t) * t * exp(-x^2/2),  t = 1 / (1 + p |x|/sqrt2)
+//   gelu(x) = max(x, 0) - (|x|/2) * c
+// and exp(-z^2) = ex2(-u^2) with u = z * sqrt(log2 e): 2 MUFU (rcp, ex2, both .ftz: no denormal fix-up code) + 13
+// FMA-pipe instructions (libm erff: ~30; the straightforward 0.5x(1+erf) form with __expf: ~20).
 __device__ __forceinline__ float gelu_erf(float x) {
 #ifdef VG_GELU_LIBM
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 #endif
-  const float z = fabsf(x) * 0.70710678118654752f;
+  constexpr float kU = 0.70710678118654752f * 1.2011224087864498f;   // 1/sqrt2 * sqrt(log2 e)
+  constexpr float kP = 0.3275911f / 1.2011224087864498f;             // p / sqrt(log2 e)
+  const float ax = fabsf(x);
+  const float u = ax * kU;
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(u, kP, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float c = poly * t * fast_exp2(-u * u);
+  return fmaxf(x, 0.f) - (0.5f * ax) * c;
 }
 
 static constexpr int kEpiStageBytes = 128 * 64;              // one staging tile: 128 rows x 32 fp16
@@ -188,7 +195,10 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
       tmem_ld_wait();
       if (t.row_ok) {
         const int wbase = t.nb_i * BN + c0;  // packed weight-row index of value j (gate is + hb)
-        float f[32];
+        // reference: the projection is an fp16 tensor, gelu(gate) an fp16 tensor, their product an fp16 tensor.
+        // Pairs are kept packed: value and gelu(gate) are rounded by the f32x2 -> f16x2 pack, the product is one
+        // HMUL2 (an fp16 x fp16 product is exact in fp32, so rounding it once is what the reference computes).
+        uint32_t o[16];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
@@ -198,30 +208,26 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
           }
           const float bva[4] = {bv.x, bv.y, bv.z, bv.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
+          for (int jj = 0; jj < 4; jj += 2) {
             const int j = j4 * 4 + jj;
-            const float a = fmaf(__uint_as_float(v[j]), e.alpha, bva[jj]);
-            const float b = fmaf(__uint_as_float(g[j]), e.alpha, bga[jj]);
-            // reference rounds the projection to fp16, gelu to fp16, product to fp16
-            const float a16 = __half2float(__float2half_rn(a));
-            const float b16 = __half2float(__float2half_rn(b));
-            const float ge = __half2float(__float2half_rn(gelu_erf(b16)));
-            f[j] = a16 * ge;
+            const __half2 a2 = __floats2half2_rn(fmaf(__uint_as_float(v[j]), e.alpha, bva[jj]),
+                                                 fmaf(__uint_as_float(v[j + 1]), e.alpha, bva[jj + 1]));
+            const float2 b2 = __half22float2(__floats2half2_rn(fmaf(__uint_as_float(g[j]), e.alpha, bga[jj]),
+                                                               fmaf(__uint_as_float(g[j + 1]), e.alpha, bga[jj + 1])));
+            const __half2 o2 = __hmul2(a2, __floats2half2_rn(gelu_erf(b2.x), gelu_erf(b2.y)));
+            o[j >> 1] = *reinterpret_cast<const uint32_t*>(&o2);
           }
         }
         if (vec_ok && full) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
-            uint4 o;
-            o.x = pack_half2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-            o.y = pack_half2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-            o.z = pack_half2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-            o.w = pack_half2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-            if (staged) epi_stage_put(st, j8, o);
-            else *reinterpret_cast<uint4*>(orow + obase + j8 * 8) = o;
+            const uint4 u4 = make_uint4(o[j8 * 4 + 0], o[j8 * 4 + 1], o[j8 * 4 + 2], o[j8 * 4 + 3]);
+            if (staged) epi_stage_put(st, j8, u4);
+            else *reinterpret_cast<uint4*>(orow + obase + j8 * 8) = u4;
           }
         } else {
-          for (int j = 0; j < 32 && obase + j < out_n; ++j) orow[obase + j] = __float2half_rn(f[j]);
+          const __half* oh = reinterpret_cast<const __half*>(o);
+          for (int j = 0; j < 32 && obase + j < out_n; ++j) orow[obase + j] = oh[j];
         }
       }
       if (staged) epi_stage_publish(st, obase, t);
