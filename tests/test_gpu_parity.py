@@ -187,3 +187,30 @@ def test_gauss_sampler_pair_parity(golden_dir, monkeypatch):
     assert lat.dtype == torch.float32 and torch.isfinite(lat).all()
     # 4 solver steps x CFG 9.0 with the 2M correction: the reference's own fp16 path sits at ~1.7e-2 here
     assert e_mine < 2.5e-2 and e_mine < 1.25 * e_ref16 + 5e-4
+
+
+def test_lcm_sampler_parity(golden_dir):
+    """BASELINE config 3 path: 4 LCM steps (CFG off) of UNetSD_VideoLCM through the LCMScheduler stand-in, against
+    the oracle restatement run with the reference-pinned UNet oracle (the scheduler itself is parity-unpinned:
+    diffusers is absent).  Both sides draw the re-noising tensors from the same device RNG stream."""
+    from oracle import lcm_oracle as lo
+    from vgen_b200.lcm import LCMScheduler
+    case, m, inp, sdg, _ = _setup(golden_dir, "videolcm_tiny")
+    sched = LCMScheduler(prediction_type="v_prediction", beta_schedule="scaled_linear", clip_sample=False,
+                         timestep_spacing="linspace", rescale_betas_zero_snr=True)
+    sched.set_timesteps(4, device="cuda")
+    torch.manual_seed(31)
+    lat = inp["x"].clone()
+    for t in sched.timesteps:
+        out = m(sched.scale_model_input(lat, t), t.repeat(lat.size(0)).to(lat.dtype), t_w=None, y=inp["y"])
+        lat = sched.step(out, t, lat, return_dict=False)[0]
+    fn = lambda xt, t, **k: vo.unet_videolcm_forward(sdg, xt, t, **k)  # noqa: E731
+    torch.manual_seed(31)
+    ref32 = lo.sample_loop(inp["x"].clone(), fn, {"y": inp["y"]}, 4)
+    torch.manual_seed(31)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref16 = lo.sample_loop(inp["x"].clone(), fn, {"y": inp["y"]}, 4)
+    e_mine, e_ref16 = _rel_l2(lat, ref32), _rel_l2(ref16, ref32)
+    print(f"lcm 4-step: ours {e_mine:.3e}; oracle-autocast {e_ref16:.3e}")
+    assert lat.dtype == torch.float32 and torch.isfinite(lat).all()
+    assert e_mine < 1e-2 and e_mine < 1.25 * e_ref16 + 5e-4

@@ -232,3 +232,23 @@ def test_brownian_tree_increments_are_consistent():
     tr2 = BrownianTree(0.1, w0, 2.1, entropy=7)                                 # same seed + same query order -> same path
     assert torch.equal(tr2(0.5, 1.0), a) and torch.equal(tr2(1.0, 1.7), b)
     assert abs(float(a.var()) - 0.5) < 0.05 and abs(float(b.var()) - 0.7) < 0.07 and abs(float((a * b).mean())) < 0.05
+
+
+def test_lcm_scheduler_host_math():
+    """LCMScheduler stand-in (diffusers is absent: parity unpinned): host tables and timestep selection
+    against the oracle restatement and the documented properties of the algorithm."""
+    from oracle import lcm_oracle as lo
+    from vgen_b200.lcm import LCMScheduler
+    s = LCMScheduler(prediction_type="v_prediction", beta_schedule="scaled_linear", clip_sample=False,
+                     timestep_spacing="linspace", rescale_betas_zero_snr=True)
+    s.set_timesteps(4, device="cpu")
+    assert s.timesteps.tolist() == [999, 759, 499, 259] == lo.lcm_timesteps(4)
+    assert torch.equal(s.alphas_cumprod, lo.alphas_cumprod(True))
+    assert float(s.alphas_cumprod[999]) == 0.0 and 0.99 < float(s.alphas_cumprod[0]) < 1.0
+    for t in (999, 259, 19):
+        assert s.boundary_scalings(t) == pytest.approx(lo.boundary_scalings(float(t)), rel=1e-12)
+    cs, co = s.boundary_scalings(0)
+    assert cs == 1.0 and co == 0.0                      # consistency boundary condition f(x, 0) = x
+    s.set_timesteps(8)
+    assert s.timesteps.tolist() == lo.lcm_timesteps(8) and len(set(s.timesteps.tolist())) == 8
+    assert torch.equal(s.scale_model_input(torch.ones(2)), torch.ones(2))

@@ -23,4 +23,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name in ("GaussianDiffusion", "DiffusionDDIMSR"):
         from . import diffusion_gauss
         return getattr(diffusion_gauss, name)
+    if name == "LCMScheduler":
+        from .lcm import LCMScheduler
+        return LCMScheduler
     raise AttributeError(name)
