@@ -182,7 +182,8 @@ assert sorted(sum(got, [])) == sorted(prompts) and all(len(g) == 4 for g in got)
 assert parallel.shard_items(prompts, rank, world, "replicate") == prompts
 assert parallel.max_over_ranks(float(rank)) == float(world - 1)
 parallel.barrier()
-print("RANK_OK", rank)
+import os
+os.write(1, f"RANK_OK_{rank}\n".encode())   # one write(2) per rank: lines of concurrent ranks cannot interleave
 '''
 
 
@@ -196,7 +197,7 @@ def test_gloo_world2_broadcast_and_sharding(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout
+    assert "RANK_OK_0" in r.stdout and "RANK_OK_1" in r.stdout
 
 
 def test_gauss_host_math_is_bit_exact(golden_dir):
