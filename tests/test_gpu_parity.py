@@ -214,3 +214,30 @@ def test_lcm_sampler_parity(golden_dir):
     print(f"lcm 4-step: ours {e_mine:.3e}; oracle-autocast {e_ref16:.3e}")
     assert lat.dtype == torch.float32 and torch.isfinite(lat).all()
     assert e_mine < 1e-2 and e_mine < 1.25 * e_ref16 + 5e-4
+
+
+def test_cfg_batching_matches_two_forwards(golden_dir, monkeypatch):
+    """diffusion.cfg_forward: one batch-2b forward for the cond / uncond branches == two separate forwards
+    (batch entries never interact; only fp32 partial-sum orders inside GroupNorm differ)."""
+    case, m, inp, sdg, gold = _setup(golden_dir, "i2vgen_tiny")
+    diff = vgen_b200.DiffusionDDIM(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+                                   mean_type="v", var_type="fixed_small")
+    kw = [{"y": inp["y"], "image": inp["image"], "local_image": inp["local_image"], "fps": inp["fps"]},
+          {"y": inp["y_neg"], "image": torch.zeros_like(inp["image"]), "local_image": inp["local_image"], "fps": inp["fps"]}]
+    calls = []
+    orig = type(m).forward
+
+    def spy(self, x, *a, **k):
+        calls.append(x.shape[0])
+        return orig(self, x, *a, **k)
+    monkeypatch.setattr(type(m), "forward", spy)
+    monkeypatch.setenv("VGEN_CFG_BATCH", "1")
+    a = diff.ddim_sample_loop(inp["x"], m, kw, guide_scale=9.0, ddim_timesteps=4, eta=0.0)
+    assert calls == [2, 2, 2, 2]
+    calls.clear()
+    monkeypatch.setenv("VGEN_CFG_BATCH", "0")
+    b = diff.ddim_sample_loop(inp["x"], m, kw, guide_scale=9.0, ddim_timesteps=4, eta=0.0)
+    assert calls == [1] * 8
+    assert _rel_l2(a, b) < 2e-3
+    truth = torch.from_numpy(gold["ddim_latent"]).cuda()
+    assert _rel_l2(a, truth) < 1.5e-2

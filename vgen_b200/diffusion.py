@@ -13,6 +13,7 @@ reward variants are out of scope and absent (calling them raises AttributeError,
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -54,6 +55,35 @@ def beta_schedule(schedule="cosine", num_timesteps=1000, zero_terminal_snr=False
 
 def _unwrap(model):
     return getattr(model, "module", model)
+
+
+def cfg_forward(model, xt, ts, model_kwargs, by_keyword=False):
+    """The two classifier-free-guidance evaluations of one step (diffusion_ddim.py:157-158, diffusion_gauss.py:204-208).
+
+    A vgen_b200 UNet (`cfg_batch = True`) evaluates both branches as ONE forward of batch 2b -- the same arithmetic
+    per sample (batch entries never interact), half the launches, and two tiles per CTA pair on the low-resolution
+    layers so their epilogue overlaps a main loop.  Any other callable (e.g. a reference model) gets the reference's
+    two separate calls.  VGEN_CFG_BATCH=0 disables the batching."""
+    kc, ku = model_kwargs
+    m = _unwrap(model)
+    call = (lambda x, t, kw: model(x, t=t, **kw)) if by_keyword else (lambda x, t, kw: model(x, t, **kw))
+    if getattr(m, "cfg_batch", False) and os.environ.get("VGEN_CFG_BATCH", "1") != "0" and kc.keys() == ku.keys():
+        merged = {}
+        for k in kc:
+            a, b = kc[k], ku[k]
+            if torch.is_tensor(a) and torch.is_tensor(b) and a.shape == b.shape and a.dtype == b.dtype and a.dim() >= 1 \
+                    and a.size(0) == xt.size(0):
+                merged[k] = torch.cat([a, b], dim=0)
+            elif a is None and b is None:
+                merged[k] = None
+            else:
+                merged = None
+                break
+        if merged is not None:
+            out = call(torch.cat([xt, xt], dim=0), torch.cat([ts, ts], dim=0), merged)
+            n = xt.size(0)
+            return out[:n], out[n:]
+    return call(xt, ts, kc), call(xt, ts, ku)
 
 
 class DiffusionDDIM(object):
@@ -129,8 +159,7 @@ class DiffusionDDIM(object):
             u_out = None
         else:
             assert isinstance(model_kwargs, list) and len(model_kwargs) == 2
-            y_out = model(xt, ts, **model_kwargs[0])
-            u_out = model(xt, ts, **model_kwargs[1])
+            y_out, u_out = cfg_forward(model, xt, ts, model_kwargs)
         coef = self.step_coefficients(step, ddim_timesteps, eta)
         noise = torch.randn_like(xt)  # the reference draws it even when eta == 0 (:237): keeps RNG streams aligned
         y16 = y_out if y_out.dtype == torch.float16 else y_out.to(torch.float16)

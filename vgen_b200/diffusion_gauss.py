@@ -20,7 +20,7 @@ import random
 import torch
 
 from . import brownian, ops
-from .diffusion import _cosine_betas, _linear_sd_betas, _rescale_zero_terminal_snr
+from .diffusion import _cosine_betas, _linear_sd_betas, _rescale_zero_terminal_snr, cfg_forward
 
 BROWNIAN_TREE = None   # override hook: a class with the torchsde.BrownianTree interface; None = default_tree_cls()
 
@@ -117,12 +117,11 @@ class GaussianDiffusion(object):
             out = _f16c(model(xt, t=t, **model_kwargs))
         else:
             assert isinstance(model_kwargs, list) and len(model_kwargs) == 2
-            y_out = _f16c(model(xt, t=t, **model_kwargs[0]))
             if guide_scale == 1.0:
-                out = y_out
+                out = _f16c(model(xt, t=t, **model_kwargs[0]))
             else:
-                u_out = _f16c(model(xt, t=t, **model_kwargs[1]))
-                out, stats = ops.cfg_combine(y_out, u_out, guide_scale)
+                y_out, u_out = cfg_forward(model, xt, t, model_kwargs, by_keyword=True)
+                out, stats = ops.cfg_combine(_f16c(y_out), _f16c(u_out), guide_scale)
                 if guide_rescale is None:
                     stats = None
                 else:

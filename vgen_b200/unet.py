@@ -59,6 +59,7 @@ class _Weights:
 
 class _UNetBase(SpecModule):
     KIND = "t2v"
+    cfg_batch = True  # samplers may evaluate the cond / uncond CFG branches as one batch-2b forward (diffusion.cfg_forward)
     WOIMG = False     # HiGen: temporal branches contribute 0 when a single frame is sampled
     SR600 = False     # SR600: (2,1)-padded downsampling, row-cropped upsampling, filtered skips
 
