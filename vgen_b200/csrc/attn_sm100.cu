@@ -11,7 +11,9 @@
 //   warps 0-3 / 4-7  softmax + output for q-tile 0 / 1 (thread r <-> TMEM lane r)
 //   warp 8           TMA producer: Q once, then separate 2-slot rings of K and V blocks of 128 keys (K(j) is
 //                    released as soon as both tiles' QK(j) ran, long before V(j))
-//   warp 9           tcgen05.mma issue (whole warp walks the loop, one elected lane issues)
+//   warps 9 / 10     tcgen05.mma issue for q-tile 0 / 1 (whole warp walks the loop, one elected lane issues); one
+//                    issuer per tile halves the event -> issue reaction time (a single warp polling both tiles'
+//                    four barriers needed ~600 cycles per round, behind the softmax warps' MUFU traffic)
 // The two q-tiles ping-pong on the tensor pipe: while the softmax warps of tile 0 work on S0(j+1), the
 // tensor core runs PV1(j) and QK1(j+1).  P is double-buffered per tile, so the exponentials of block j never
 // wait for PV(j-1) (that wait was 23% of the softmax warps' time with a single P buffer: the PV round trip
@@ -28,7 +30,7 @@
 
 namespace vg {
 
-static constexpr int kAttnThreads = 320;
+static constexpr int kAttnThreads = 352;
 static constexpr int kD = 64;
 static constexpr int kTileQ = 128;   // rows per q-tile (UMMA M)
 static constexpr int kTileK = 128;   // keys per block (UMMA N of QK^T)
@@ -83,9 +85,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
     mbar_init(q_full, 1);
     for (int i = 0; i < kKvStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);   // one commit per tile's issuer
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -146,65 +148,56 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
         else if (clock64() - t_idle > VG_WATCHDOG_CYCLES) mbar_deadlock(10, 0);
       }
     }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issue (warp-uniform loop)
+  } else if (warp >= 9) {
+    // ------------------------------------------------------------------ MMA issue for q-tile i (warp-uniform loop)
+    const int i = warp - 9;
     const uint32_t idesc_qk = umma_idesc_f16(kTileQ, kTileK, 0, 0);
     const uint32_t idesc_pv = umma_idesc_f16(kTileQ, kD, 0, 1);  // B (= V) is MN-major
-    const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr0 = smem_u32(sV), p_addr0 = smem_u32(sP);
-    auto issue_qk = [&](int i, int j, bool release_k) {
-      if (elect_one()) {
-        const uint64_t a_desc = umma_desc_sw128(q_addr + i * kQBytes, 16, 1024);
-        const uint64_t b_desc = umma_desc_sw128(k_addr + (j & 1) * kKBytes, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_f16_ss(tmem + i * 128, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[i]);
-        if (release_k) umma_commit(&k_empty[j & 1]);  // K(j) consumed by both tiles
-      }
-      __syncwarp();
-    };
-    // Event-driven issue: QK_i(j+1) goes out as soon as the softmax warps of tile i have pulled S_i(j) into
-    // registers (s_free), i.e. it overlaps their exponentials; PV_i(j) goes out when P_i(j) is in shared memory.
-    auto issue_pv = [&](int i, int j, bool release_kv) {
-      if (elect_one()) {
-        const int st = j & 1;
-        const uint32_t v_addr = v_addr0 + st * kKBytes;
-        const uint32_t p_addr = p_addr0 + (2 * i + (j & 1)) * kPBytes;
-#pragma unroll
-        for (int ks = 0; ks < kTileK / 16; ++ks) {
-          // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
-          const uint64_t a_desc = umma_desc_sw128(p_addr + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 16, 1024);
-          // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart
-          const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
-          umma_f16_ss(tmem + 256 + i * 64, a_desc, b_desc, idesc_pv, (j | ks) != 0);  // O accumulates over blocks
-        }
-        umma_commit(&o_full[2 * i + (j & 1)]);
-        if (release_kv) umma_commit(&v_empty[st]);  // V(j) consumed by both tiles
-      }
-      __syncwarp();
-    };
+    const uint32_t q_addr = smem_u32(sQ) + i * kQBytes, k_addr = smem_u32(sK), v_addr0 = smem_u32(sV);
+    const uint32_t p_addr0 = smem_u32(sP) + 2 * i * kPBytes;
+    const uint32_t t_s = tmem + i * 128, t_o = tmem + 256 + i * 64;
+    // Event-driven issue: QK(j+1) goes out as soon as the softmax warps of this tile have pulled S(j) into registers
+    // (s_free), i.e. it overlaps their exponentials; PV(j) goes out when P(j) is in shared memory.
     mbar_wait(q_full, 0, 11);
-    int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
+    int qk_next = 0, pv_next = 0;
     long long t_idle = 0;
-    while (pv_next[0] < nkv || pv_next[1] < nkv) {
+    while (pv_next < nkv) {
       bool progressed = false;
+      if (qk_next < nkv && (qk_next == 0 || mbar_test_wait(&s_free[i], (qk_next - 1) & 1)) &&
+          mbar_test_wait(&k_full[qk_next & 1], (qk_next >> 1) & 1)) {
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = umma_desc_sw128(q_addr, 16, 1024);
+          const uint64_t b_desc = umma_desc_sw128(k_addr + (qk_next & 1) * kKBytes, 16, 1024);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int jq = qk_next[i];
-        if (jq < nkv && (jq == 0 || mbar_test_wait(&s_free[i], (jq - 1) & 1)) &&
-            mbar_test_wait(&k_full[jq & 1], (jq >> 1) & 1)) {
-          tc_fence_after();
-          issue_qk(i, jq, qk_next[1 - i] > jq);
-          qk_next[i] = jq + 1;
-          progressed = true;
+          for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[i]);
+          umma_commit(&k_empty[qk_next & 1]);  // this tile is done with K(j); the slot frees when both tiles are
         }
-        const int jp = pv_next[i];
-        if (jp < nkv && mbar_test_wait(&p_full[2 * i + (jp & 1)], (jp >> 1) & 1) &&
-            mbar_test_wait(&v_full[jp & 1], (jp >> 1) & 1)) {
-          tc_fence_after();
-          issue_pv(i, jp, pv_next[1 - i] > jp);
-          pv_next[i] = jp + 1;
-          progressed = true;
+        __syncwarp();
+        ++qk_next;
+        progressed = true;
+      }
+      if (pv_next < nkv && mbar_test_wait(&p_full[2 * i + (pv_next & 1)], (pv_next >> 1) & 1) &&
+          mbar_test_wait(&v_full[pv_next & 1], (pv_next >> 1) & 1)) {
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t v_addr = v_addr0 + (pv_next & 1) * kKBytes;
+          const uint32_t p_addr = p_addr0 + (pv_next & 1) * kPBytes;
+#pragma unroll
+          for (int ks = 0; ks < kTileK / 16; ++ks) {
+            // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
+            const uint64_t a_desc = umma_desc_sw128(p_addr + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 16, 1024);
+            // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart
+            const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
+            umma_f16_ss(t_o, a_desc, b_desc, idesc_pv, (pv_next | ks) != 0);  // O accumulates over blocks
+          }
+          umma_commit(&o_full[2 * i + (pv_next & 1)]);
+          umma_commit(&v_empty[pv_next & 1]);
         }
+        __syncwarp();
+        ++pv_next;
+        progressed = true;
       }
       if (progressed) {
         t_idle = 0;
