@@ -158,53 +158,47 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
     const uint32_t t_s = tmem + i * 128, t_o = tmem + 256 + i * 64;
     // Event-driven issue: QK(j+1) goes out as soon as the softmax warps of this tile have pulled S(j) into registers
     // (s_free), i.e. it overlaps their exponentials; PV(j) goes out when P(j) is in shared memory.
+    // Per tile the events arrive in a fixed order -- s_free(j) (scores in registers) always precedes p_full(j) (P
+    // written) -- so the issuer simply blocks on them in turn (hardware-assisted mbarrier wait: no polling loop
+    // competing with the softmax warps for issue slots, and a short wake-up):  QK(0); { QK(j+1); PV(j) } ...
+    auto issue_qk = [&](int j) {
+      mbar_wait(&k_full[j & 1], (j >> 1) & 1, 12);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t a_desc = umma_desc_sw128(q_addr, 16, 1024);
+        const uint64_t b_desc = umma_desc_sw128(k_addr + (j & 1) * kKBytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[i]);
+        umma_commit(&k_empty[j & 1]);  // this tile is done with K(j); the slot frees when both tiles are
+      }
+      __syncwarp();
+    };
     mbar_wait(q_full, 0, 11);
-    int qk_next = 0, pv_next = 0;
-    long long t_idle = 0;
-    while (pv_next < nkv) {
-      bool progressed = false;
-      if (qk_next < nkv && (qk_next == 0 || mbar_test_wait(&s_free[i], (qk_next - 1) & 1)) &&
-          mbar_test_wait(&k_full[qk_next & 1], (qk_next >> 1) & 1)) {
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t a_desc = umma_desc_sw128(q_addr, 16, 1024);
-          const uint64_t b_desc = umma_desc_sw128(k_addr + (qk_next & 1) * kKBytes, 16, 1024);
+    issue_qk(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) {
+        mbar_wait(&s_free[i], j & 1, 13);
+        issue_qk(j + 1);
+      }
+      mbar_wait(&p_full[2 * i + (j & 1)], (j >> 1) & 1, 14);
+      mbar_wait(&v_full[j & 1], (j >> 1) & 1, 15);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t v_addr = v_addr0 + (j & 1) * kKBytes;
+        const uint32_t p_addr = p_addr0 + (j & 1) * kPBytes;
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
-          umma_commit(&s_full[i]);
-          umma_commit(&k_empty[qk_next & 1]);  // this tile is done with K(j); the slot frees when both tiles are
+        for (int ks = 0; ks < kTileK / 16; ++ks) {
+          // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
+          const uint64_t a_desc = umma_desc_sw128(p_addr + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 16, 1024);
+          // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart
+          const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
+          umma_f16_ss(t_o, a_desc, b_desc, idesc_pv, (j | ks) != 0);  // O accumulates over blocks
         }
-        __syncwarp();
-        ++qk_next;
-        progressed = true;
+        umma_commit(&o_full[2 * i + (j & 1)]);
+        umma_commit(&v_empty[j & 1]);
       }
-      if (pv_next < nkv && mbar_test_wait(&p_full[2 * i + (pv_next & 1)], (pv_next >> 1) & 1) &&
-          mbar_test_wait(&v_full[pv_next & 1], (pv_next >> 1) & 1)) {
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t v_addr = v_addr0 + (pv_next & 1) * kKBytes;
-          const uint32_t p_addr = p_addr0 + (pv_next & 1) * kPBytes;
-#pragma unroll
-          for (int ks = 0; ks < kTileK / 16; ++ks) {
-            // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
-            const uint64_t a_desc = umma_desc_sw128(p_addr + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 16, 1024);
-            // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart
-            const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
-            umma_f16_ss(t_o, a_desc, b_desc, idesc_pv, (pv_next | ks) != 0);  // O accumulates over blocks
-          }
-          umma_commit(&o_full[2 * i + (pv_next & 1)]);
-          umma_commit(&v_empty[pv_next & 1]);
-        }
-        __syncwarp();
-        ++pv_next;
-        progressed = true;
-      }
-      if (progressed) {
-        t_idle = 0;
-      } else {
-        if (t_idle == 0) t_idle = clock64();
-        else if (clock64() - t_idle > VG_WATCHDOG_CYCLES) mbar_deadlock(15, 0);
-      }
+      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- softmax / output warps
