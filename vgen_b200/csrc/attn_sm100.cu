@@ -118,35 +118,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       tma_load_4d(sQ + kQBytes, &p.map_q, q_full, 0, head, q0 + kTileQ, batch);
     }
     __syncwarp();
-    // K and V rings are filled independently, whichever slot frees first (use u of slot s is block 2u + s)
-    int k_next = 0, v_next = 0;
-    long long t_idle = 0;
-    while (k_next < nkv || v_next < nkv) {
-      bool progressed = false;
-      if (k_next < nkv && (k_next < kKvStages || mbar_test_wait(&k_empty[k_next & 1], ((k_next >> 1) - 1) & 1))) {
-        if (elect_one()) {
-          mbar_expect_tx(&k_full[k_next & 1], kKBytes);
-          tma_load_4d(sK + (k_next & 1) * kKBytes, &p.map_k, &k_full[k_next & 1], 0, head, k_next * kTileK, kvb);
-        }
-        __syncwarp();
-        ++k_next;
-        progressed = true;
+    // K(j) then V(j), blocking on the slot's release (use u of slot s is block 2u + s).  K(j)'s slot frees after both
+    // tiles' QK(j-2), V(j)'s after both PV(j-2) -- each at least a block before the data is needed again.
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      if (j >= kKvStages) mbar_wait(&k_empty[st], ((j >> 1) - 1) & 1, 10);
+      if (elect_one()) {
+        mbar_expect_tx(&k_full[st], kKBytes);
+        tma_load_4d(sK + st * kKBytes, &p.map_k, &k_full[st], 0, head, j * kTileK, kvb);
       }
-      if (v_next < nkv && (v_next < kKvStages || mbar_test_wait(&v_empty[v_next & 1], ((v_next >> 1) - 1) & 1))) {
-        if (elect_one()) {
-          mbar_expect_tx(&v_full[v_next & 1], kKBytes);
-          tma_load_4d(sV + (v_next & 1) * kKBytes, &p.map_v, &v_full[v_next & 1], 0, head, v_next * kTileK, kvb);
-        }
-        __syncwarp();
-        ++v_next;
-        progressed = true;
+      __syncwarp();
+      if (j >= kKvStages) mbar_wait(&v_empty[st], ((j >> 1) - 1) & 1, 16);
+      if (elect_one()) {
+        mbar_expect_tx(&v_full[st], kKBytes);
+        tma_load_4d(sV + st * kKBytes, &p.map_v, &v_full[st], 0, head, j * kTileK, kvb);
       }
-      if (progressed) {
-        t_idle = 0;
-      } else {
-        if (t_idle == 0) t_idle = clock64();
-        else if (clock64() - t_idle > VG_WATCHDOG_CYCLES) mbar_deadlock(10, 0);
-      }
+      __syncwarp();
     }
   } else if (warp >= 9) {
     // ------------------------------------------------------------------ MMA issue for q-tile i (warp-uniform loop)
