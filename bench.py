@@ -246,6 +246,25 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(kernels):
+    """DRAM bytes per launch of a kernel family, from the committed ncu launch list of this same command
+    (profiles/<tag>_traffic.json, written by tools/ncu_summary.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        d = json.load(open(files[-1]))
+        hit = [k for k in d if k.startswith(tuple(kernels))]       # template instantiations share the prefix
+        n = sum(d[k]["launches"] for k in hit)
+        b = sum(d[k]["launches"] * (d[k]["dram_read_bytes_per_launch"] + d[k]["dram_write_bytes_per_launch"]) for k in hit)
+        if n == 0 or b == 0:
+            return None
+        return {"bytes_per_launch": b / n, "source": "profiles/" + os.path.basename(files[-1])}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,6 +429,12 @@ def main():
                         "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
                         "launches_per_step": tg["launches"], "avg_launch_ms": tg["ms"] / tg["launches"],
                         "algorithmic_tflop_per_step": tg["flops"] / 1e12, "peak_source": pk["source"]}
+            tr = ncu_traffic(("tapgemm_sm100_2cta_kernel", "tapgemm_sm100_kernel"))
+            if tr:
+                roofline["traffic"] = tr["bytes_per_launch"]
+                roofline["traffic_unit"] = "DRAM bytes / launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+                roofline["traffic_source"] = tr["source"]
+                roofline["algorithmic_bytes_per_launch"] = tg["bytes"] / tg["launches"]
 
     value = world * args.steps / (ms_max / 1e3)
     line = {"metric": "denoise_steps_per_s", "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": args.steps,

@@ -1,6 +1,6 @@
 """Summarise ncu artefacts into markdown for profiles/ (run in the build container; ncu only reads files).
 
-  python tools/ncu_summary.py launches gpurun_out/launches_r01k.csv            > profiles/r01k_launches.md
+  python tools/ncu_summary.py launches gpurun_out/launches_r01k.csv [profiles/r01k_traffic.json] > profiles/r01k_launches.md
   python tools/ncu_summary.py report   gpurun_out/prof_tapgemm_r01k.ncu-rep ... > profiles/r01k_ncu_summary.md
 """
 from __future__ import annotations
@@ -41,27 +41,41 @@ def _num(x):
         return 0.0
 
 
-def launches(path):
+def launches(path, json_out=None):
     rows = list(csv.reader(open(path)))
     start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[start]
     ix = {h: i for i, h in enumerate(hdr)}
-    agg = collections.defaultdict(lambda: [0, 0.0])
+    agg = collections.defaultdict(lambda: {"ids": set(), "ns": 0.0, "rd": 0.0, "wr": 0.0})
     for r in rows[start + 1:]:
         if len(r) != len(hdr):
             continue
         name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("vg::", "")
-        agg[name][0] += 1
-        agg[name][1] += _num(r[ix["Metric Value"]])
-    tot = sum(v[1] for v in agg.values())
-    print(f"# kernel launch list ({path.split('/')[-1]}): `ncu --metrics gpu__time_duration.sum --clock-control none`")
+        a = agg[name]
+        a["ids"].add(r[ix["ID"]])
+        metric, unit, val = r[ix["Metric Name"]], r[ix["Metric Unit"]], _num(r[ix["Metric Value"]])
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6}.get(unit, 1.0)
+        if metric.startswith("gpu__time_duration"):
+            a["ns"] += val * scale
+        elif metric.startswith("dram__bytes_read"):
+            a["rd"] += val * scale
+        elif metric.startswith("dram__bytes_write"):
+            a["wr"] += val * scale
+    tot = sum(v["ns"] for v in agg.values())
+    print(f"# kernel launch list ({path.split('/')[-1]}): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none`")
     print("\nPer-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's live breakdown, not absolutes.\n")
-    print("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        if v[1] / tot < 0.0005:
+    print("| kernel | launches | total us | share | DRAM read MB / launch | DRAM write MB / launch |\n|---|---:|---:|---:|---:|---:|")
+    out = {}
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
+        n = len(v["ids"])
+        out[k] = {"launches": n, "us": v["ns"] / 1e3, "dram_read_bytes_per_launch": v["rd"] / n, "dram_write_bytes_per_launch": v["wr"] / n}
+        if v["ns"] / tot < 0.0005:
             continue
-        print(f"| `{k}` | {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f}% |")
-    print(f"\ntotal {tot / 1e6:.2f} ms over {sum(v[0] for v in agg.values())} launches (one UNet forward + the step update)")
+        print(f"| `{k}` | {n} | {v['ns'] / 1e3:.1f} | {100 * v['ns'] / tot:.1f}% | {v['rd'] / n / 1e6:.2f} | {v['wr'] / n / 1e6:.2f} |")
+    print(f"\ntotal {tot / 1e6:.2f} ms over {sum(len(v['ids']) for v in agg.values())} launches (one CFG-batched UNet forward + the step update)")
+    if json_out:
+        import json
+        json.dump(out, open(json_out, "w"), indent=1)
 
 
 def report(path):
@@ -95,7 +109,7 @@ def report(path):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2])
+        launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         print("# ncu summaries\n\nRead with `ncu -i <rep> --page raw|source --csv`; the .ncu-rep files stay in gpurun_out/ (scratch).")
         for p in sys.argv[2:]:

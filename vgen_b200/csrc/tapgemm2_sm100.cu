@@ -34,6 +34,7 @@ struct alignas(64) TapGemm2Params {
   int total_pair_tiles;  // ceil(m_tiles / 2) * nb
 };
 
+template <bool kGeglu>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     tapgemm_sm100_2cta_kernel(const __grid_constant__ TapGemm2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -160,7 +161,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int rows_in_tile = s.box1 * s.box2;
-    const int out_n = e.geglu ? (s.n >> 1) : s.n;
+    const int out_n = kGeglu ? (s.n >> 1) : s.n;
     const bool vec_ok = tapgemm_vec_ok(e, out_n);
     int r1, r2;                       // position of this thread's row inside the box (tile-invariant)
     fd_divmod(s.f_box1, r, r2, r1);
@@ -189,7 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       const int i2 = t.i2_0 + r2;
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2) && (t.i3 < s.d3);
       t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
-      if (e.residual && t.row_ok && !e.geglu) {
+      if (!kGeglu && e.residual && t.row_ok) {
         // the residual row segment comes from HBM: start pulling it into L2 while the tile's MMAs are still running
         const __half* rp = e.residual + t.row * e.ldr + t.nb_i * BN;
         for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN && t.nb_i * BN + c0 < s.n; c0 += 64)
@@ -198,7 +199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       mbar_wait(&tfull_bar[as], aph, 34);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, est, vec_ok, out_n, cg, 2);
+      tapgemm_epilogue_tile<kGeglu>(s, e, t, est, vec_ok, out_n, cg, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
@@ -267,13 +268,15 @@ int tapgemm_sm100_2cta_launch(const TapGemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   int clusters = sm_count() / 2;
   if (clusters > p.total_pair_tiles) clusters = p.total_pair_tiles;
   if (clusters < 1) return 0;
-  tapgemm_sm100_2cta_kernel<<<2 * clusters, kThreads2, smem, stream>>>(p);
+  if (a.epi.geglu) tapgemm_sm100_2cta_kernel<true><<<2 * clusters, kThreads2, smem, stream>>>(p);
+  else tapgemm_sm100_2cta_kernel<false><<<2 * clusters, kThreads2, smem, stream>>>(p);
   VG_LAUNCH_CHECK("tapgemm_sm100_2cta_kernel");
   return 0;
 }

@@ -106,10 +106,13 @@ __device__ __forceinline__ void epi_stage_drain(const EpiStore& st) {
 
 // chunk0 / chunk_step: this warp handles the 32-column chunks chunk0, chunk0 + chunk_step, ... (two warps share
 // a TMEM lane quadrant and split the columns between them).
+// kGeglu is a template parameter of the kernels: the two epilogues have very different register needs, and
+// compiled into one kernel each paid for the other's allocation and schedule.
+template <bool kGeglu>
 __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, const TapGemmEpilogue& e, const EpiRow& t,
                                                       EpiStore& st, bool vec_ok, int out_n, int chunk0, int chunk_step) {
   const int BN = s.bn;
-  if (!e.geglu) {
+  if constexpr (!kGeglu) {
     const int n0 = t.nb_i * BN;
     __half* orow = e.out + t.row * e.ldo;
     const __half* rrow = e.residual ? e.residual + t.row * e.ldr : nullptr;

@@ -45,6 +45,7 @@ struct alignas(64) TapGemmKernelParams {
   int b_slot_bytes;  // smem bytes reserved per stage for the W tile (>= BN*128, multiple of 1024)
 };
 
+template <bool kGeglu>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid_constant__ TapGemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment is required by the 128B swizzle atom (8 rows x 128 B).
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;
     const int rows_in_tile = s.box1 * s.box2;
-    const int out_n = e.geglu ? (s.n >> 1) : s.n;
+    const int out_n = kGeglu ? (s.n >> 1) : s.n;
     const bool vec_ok = tapgemm_vec_ok(e, out_n);
     int r1, r2;                       // position of this thread's row inside the box (tile-invariant)
     fd_divmod(s.f_box1, r, r2, r1);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
       t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
 
-      if (e.residual && t.row_ok && !e.geglu) {
+      if (!kGeglu && e.residual && t.row_ok) {
         // the residual row segment comes from HBM: start pulling it into L2 while the tile's MMAs are still running
         const __half* rp = e.residual + t.row * e.ldr + t.nb_i * BN;
         for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN && t.nb_i * BN + c0 < s.n; c0 += 64)
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile(s, e, t, est, vec_ok, out_n, cg, 2);
+      tapgemm_epilogue_tile<kGeglu>(s, e, t, est, vec_ok, out_n, cg, 2);
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -272,13 +273,15 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   int grid = sm_count();
   if (grid > s.total_tiles) grid = s.total_tiles;
   if (grid < 1) return 0;
-  tapgemm_sm100_kernel<<<grid, kThreads, smem, stream>>>(p);
+  if (a.epi.geglu) tapgemm_sm100_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+  else tapgemm_sm100_kernel<false><<<grid, kThreads, smem, stream>>>(p);
   VG_LAUNCH_CHECK("tapgemm_sm100_kernel");
   return 0;
 }
