@@ -126,11 +126,16 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
       const bool fast = vec_ok && t.row_ok && full;
       // issue the (HBM / L2 latency) residual and per-frame-bias loads before blocking on the TMEM load
       uint4 r4[4], g4[4];
+      float4 b4[8];
       if (fast) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           if (rrow) r4[j8] = __ldg(reinterpret_cast<const uint4*>(rrow + nbase + j8 * 8));
           if (grow) g4[j8] = __ldg(reinterpret_cast<const uint4*>(grow + nbase + j8 * 8));
+          if (e.bias) {  // vec_ok implies n % 8 == 0; bias tensors are 16-byte aligned
+            b4[2 * j8] = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8));
+            b4[2 * j8 + 1] = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8 + 4));
+          }
         }
       }
       const bool staged = st.tma && vec_ok && full;  // uniform over the column group
@@ -142,9 +147,8 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * e.alpha;
-          if (e.bias) {  // vec_ok implies n % 8 == 0; bias tensors are 16-byte aligned
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8 + 4));
+          if (e.bias) {
+            const float4 b0 = b4[2 * j8], b1 = b4[2 * j8 + 1];
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
