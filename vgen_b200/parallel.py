@@ -23,9 +23,11 @@ def init_from_env(backend=None):
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
+        kw = {}
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend, rank=rank, world_size=world)
+            kw["device_id"] = torch.device("cuda", local_rank)   # binds the communicator to this GPU (no barrier() guess)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, world, local_rank
 
 
