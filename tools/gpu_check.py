@@ -187,7 +187,7 @@ def group_norm_checks():
             report(f"group_norm n{n} p{p} c{c} silu{int(silu)} shift{shift}", rel_err(y, ref.permute(0, 2, 1)), 2e-3)
         run_case(f"gn {n} {p} {c}", f)
 
-    for (rows, c) in [(1000, 320), (777, 640), (4096, 1280), (100, 512), (5000, 4), (33, 2560), (64, 64)]:
+    for (rows, c) in [(1000, 320), (1001, 320), (3, 320), (777, 640), (4096, 1280), (100, 512), (5000, 4), (33, 2560), (64, 64)]:
         def f():
             x = rnd(rows, c, scale=2.0, shift=0.3).half()
             ga, be = rnd(c, scale=0.2, shift=1.0), rnd(c, scale=0.2)

@@ -25,3 +25,21 @@ for (n, p, c, silu) in [(16, 14080, 640, True), (1, 225280, 320, True), (16, 140
     ts.sort()
     ms = ts[2]
     print({"shape": (n, p, c), "ms": round(ms, 4), "GBs_rw": round(4.0 * x.numel() / ms / 1e6, 1), "GBs_3pass": round(6.0 * x.numel() / ms / 1e6, 1)}, flush=True)
+
+for (rows, c) in [(450560, 320), (112640, 640), (28160, 1280)]:
+    x = torch.randn(rows, c, generator=g).half().cuda()
+    ga, be = torch.randn(c, generator=g).cuda(), torch.randn(c, generator=g).cuda()
+    y = torch.empty_like(x)
+    fn = lambda: ops.layer_norm(x, ga, be, out=y)  # noqa: E731
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    print({"layer_norm": (rows, c), "ms": round(ts[2], 4), "GBs_rw": round(4.0 * x.numel() / ts[2] / 1e6, 1)}, flush=True)

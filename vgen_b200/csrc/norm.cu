@@ -343,6 +343,104 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   }
 }
 
+// read-only 16-byte load the compiler may not hoist out of a loop (ptxas kept 80 loop-invariant gamma / beta values in
+// registers and spilled; the lines stay L1-resident, re-loading them per row group is cheaper than the lost occupancy)
+__device__ __forceinline__ float4 ldg_f4_pinned(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// Rows narrower than a warp's worth of 16-byte vectors (C = 320 / 640: 40 / 80 vectors): LPR lanes share a row and a
+// warp normalises 32/LPR rows at once, so every load instruction is fully populated and each lane keeps VPL (= 5)
+// 16-byte loads in flight (the warp-per-row kernel had 1.25 per lane at C = 320 and ran at 3.9 TB/s).
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                long rows, int C, long ldx, long ldy, float eps) {
+  constexpr int RW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const long warps_total = (long)gridDim.x * (blockDim.x >> 5);
+  long grp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long ngroups = (rows + RW - 1) / RW;
+  if (grp >= ngroups) return;
+  uint4 nxt[VPL];
+  {
+    const long row = grp * RW + sub;
+    if (row < rows) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) nxt[j] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + (li + j * LPR) * 8));
+    }
+  }
+  for (; grp < ngroups; grp += warps_total) {
+    const long row = grp * RW + sub;
+    const bool live = row < rows;
+    uint4 cur[VPL];  // the row stays packed (fp16) in registers; each pass converts on the fly
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      cur[j] = live ? nxt[j] : make_uint4(0u, 0u, 0u, 0u);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&cur[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = __half22float2(h2[k]);
+        s += t.x + t.y;
+      }
+    }
+    const long nrow = (grp + warps_total) * RW + sub;
+    if (grp + warps_total < ngroups && nrow < rows) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) nxt[j] = __ldg(reinterpret_cast<const uint4*>(x + nrow * ldx + (li + j * LPR) * 8));
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&cur[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = __half22float2(h2[k]);
+        const float d0 = t.x - mean, d1 = t.y - mean;
+        q = fmaf(d0, d0, q);
+        q = fmaf(d1, d1, q);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    if (live) {
+      __half* yr = y + row * ldy;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int v = li + j * LPR;
+        const float4 g0 = ldg_f4_pinned(gamma + v * 8);
+        const float4 g1 = ldg_f4_pinned(gamma + v * 8 + 4);
+        const float4 b0 = ldg_f4_pinned(beta + v * 8);
+        const float4 b1 = ldg_f4_pinned(beta + v * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const __half2* h2 = reinterpret_cast<const __half2*>(&cur[j]);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t = __half22float2(h2[k]);
+          o[2 * k] = fmaf((t.x - mean) * rstd, gg[2 * k], bb[2 * k]);
+          o[2 * k + 1] = fmaf((t.y - mean) * rstd, gg[2 * k + 1], bb[2 * k + 1]);
+        }
+        uint4 u;
+        u.x = pack_half2(o[0], o[1]);
+        u.y = pack_half2(o[2], o[3]);
+        u.z = pack_half2(o[4], o[5]);
+        u.w = pack_half2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(yr + v * 8) = u;
+      }
+    }
+  }
+}
+
 // generic small-C LayerNorm (any C, scalar): one thread per row
 __global__ void layernorm_small_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, long rows, int C,
@@ -431,6 +529,17 @@ int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx
     const long cap = 16L * sm_count();  // grid-stride: ~16 resident blocks' worth per SM
     if (blocks > cap) blocks = cap;
     const int c8 = (int)c / 8;
+    if (c8 == 40 || c8 == 80) {
+      const int rw = c8 == 40 ? 4 : 2;  // rows per warp
+      long gblocks = ((rows + rw - 1) / rw + wpb - 1) / wpb;
+      if (gblocks > cap) gblocks = cap;
+      if (c8 == 40)
+        layernorm_grouped_kernel<8, 5><<<(unsigned)gblocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      else
+        layernorm_grouped_kernel<16, 5><<<(unsigned)gblocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      VG_LAUNCH_CHECK("layernorm_grouped_kernel");
+      return 0;
+    }
     if (c8 <= 32)
       layernorm_kernel<1><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     else if (c8 <= 64)
