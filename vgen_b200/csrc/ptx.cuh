@@ -135,6 +135,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// same, destination given as a shared-window address (the void* argument is ignored)
+__device__ __forceinline__ void tma_load_4d(void*, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            uint32_t smem_dst_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_dst_addr),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
                                             int c1, int c2, int c3) {
   asm volatile(

@@ -64,6 +64,13 @@ struct EpiStore {
   int bar_id;              // named barrier of the column group (128 threads)
   bool leader;             // the one thread of the group that issues / tracks the bulk stores
   uint32_t slot;           // ring position, carried across chunks and tiles
+  // residual tiles arrive by TMA as well (same box / swizzle as the output), one chunk ahead of their use
+  bool res_tma;
+  const CUtensorMap* map_res;
+  uint32_t rstage;         // shared address of this group's two residual tiles
+  uint64_t* rbar;          // [2] full barriers of those tiles
+  uint32_t box_bytes;      // bytes one residual tile load delivers (box1 * box2 * 64)
+  uint32_t r_issue, r_cons;  // loads issued / consumed so far (slot = count & 1, phase = (count >> 1) & 1)
 };
 
 __device__ __forceinline__ bool tapgemm_vec_ok(const TapGemmEpilogue& e, int out_n) {
@@ -99,6 +106,27 @@ __device__ __forceinline__ void epi_stage_publish(EpiStore& st, int col, const E
   }
   st.slot ^= 1;
 }
+// residual tile for the chunk at column `col` of tile t: issued by the group leader one chunk ahead (or, for a tile's
+// first chunk, before the accumulator-ready wait); every thread counts the issue so the slot / phase stay in step
+__device__ __forceinline__ void epi_res_issue(EpiStore& st, int col, const EpiRow& t) {
+  if (st.leader) {
+    uint64_t* bar = st.rbar + (st.r_issue & 1);
+    mbar_expect_tx(bar, st.box_bytes);
+    tma_load_4d(reinterpret_cast<void*>(0), st.map_res, bar, col, t.i1_0, t.i2_0, t.i3, st.rstage + (st.r_issue & 1) * kEpiStageBytes);
+  }
+  ++st.r_issue;
+}
+// wait for the oldest outstanding residual tile and fetch piece j8 of this thread's row
+__device__ __forceinline__ void epi_res_wait(const EpiStore& st) {
+  mbar_wait(st.rbar + (st.r_cons & 1), (st.r_cons >> 1) & 1, 35);
+}
+__device__ __forceinline__ uint4 epi_res_get(const EpiStore& st, int j8) {
+  const uint32_t addr = st.rstage + (st.r_cons & 1) * kEpiStageBytes + st.row_off + ((((uint32_t)j8) ^ st.row_xor) << 4);
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 // before the kernel exits every bulk store must have completed
 __device__ __forceinline__ void epi_stage_drain(const EpiStore& st) {
   if (st.tma && st.leader) bulk_wait_group<0>();
@@ -127,10 +155,17 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
       // issue the (HBM / L2 latency) residual and per-frame-bias loads before blocking on the TMEM load
       uint4 r4[4], g4[4];
       float4 b4[8];
+      const bool staged = st.tma && vec_ok && full;  // uniform over the column group
+      const bool res_tile = st.res_tma && staged;    // this chunk's residual was requested by TMA
+      if (res_tile) {
+        // request the NEXT chunk of this tile (its slot was last read two chunks ago, before a publish barrier)
+        const int nnext = nbase + chunk_step * 32;
+        if (c0 + chunk_step * 32 < BN && nnext + 32 <= s.n) epi_res_issue(st, nnext, t);
+      }
       if (fast) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-          if (rrow) r4[j8] = __ldg(reinterpret_cast<const uint4*>(rrow + nbase + j8 * 8));
+          if (rrow && !res_tile) r4[j8] = __ldg(reinterpret_cast<const uint4*>(rrow + nbase + j8 * 8));
           if (grow) g4[j8] = __ldg(reinterpret_cast<const uint4*>(grow + nbase + j8 * 8));
           if (e.bias) {  // vec_ok implies n % 8 == 0; bias tensors are 16-byte aligned
             b4[2 * j8] = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8));
@@ -138,8 +173,15 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
           }
         }
       }
-      const bool staged = st.tma && vec_ok && full;  // uniform over the column group
       if (staged) epi_stage_acquire(st);
+      if (res_tile) {
+        epi_res_wait(st);
+        if (fast) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) r4[j8] = epi_res_get(st, j8);
+        }
+        ++st.r_cons;
+      }
       tmem_ld_wait();
       if (fast) {
 #pragma unroll

@@ -39,6 +39,9 @@ struct alignas(64) TapGemmKernelParams {
   CUtensorMap map_b;
   CUtensorMap map_out;  // output, box {32, box1, box2, 1}, 64B swizzle (TMA tile stores of the epilogue)
   int out_tma;          // 1: map_out is valid
+  CUtensorMap map_res;  // residual, same box / swizzle as map_out (valid when res_tma)
+  int res_tma;
+  int staging_bytes;    // kEpiStagingTotal, doubled when residual tiles are staged too
   TapGemmShape s;
   TapGemmEpilogue e;
   int stages;
@@ -58,12 +61,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
 
   uint8_t* tiles = smem;
   uint8_t* staging = smem + (size_t)stages * stage_bytes;   // epilogue staging tiles (1024-aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiStagingTotal);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.staging_bytes);
   uint64_t* full_bar = bars;                 // [stages]
   uint64_t* empty_bar = bars + stages;       // [stages]
   uint64_t* tfull_bar = bars + 2 * stages;   // [2]
   uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint64_t* res_bar = bars + 2 * stages + 6;      // [2 column groups][2 slots] residual tiles landed
 
   const TapGemmShape& s = p.s;
   const int k_iters = s.num_taps * s.kc;
@@ -74,6 +78,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
     if (p.out_tma) tma_prefetch_desc(&p.map_out);
+    if (p.res_tma) tma_prefetch_desc(&p.map_res);
+    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -178,6 +184,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
     est.bar_id = 1 + cg;
     est.leader = (r == 0);
     est.slot = 0;
+    est.res_tma = !kGeglu && p.res_tma != 0;
+    est.map_res = &p.map_res;
+    est.rstage = smem_u32(staging) + kEpiStagingTotal + (uint32_t)cg * 2u * kEpiStageBytes;
+    est.rbar = res_bar + 2 * cg;
+    est.box_bytes = (uint32_t)(s.box1 * s.box2 * 64);
+    est.r_issue = est.r_cons = 0;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < s.total_tiles; tile += gridDim.x, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
@@ -193,10 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       t.row_ok = (r < rows_in_tile) && (i1 < s.d1) && (i2 < s.d2);
       t.row = ((long)t.i3 * s.d2 + i2) * s.d1 + i1;
 
-      if (!kGeglu && e.residual && t.row_ok) {
+      if (!kGeglu && est.res_tma) {
+        // the residual tile of this group's first chunk: requested now, while the tile's MMAs are still running
+        const int col = t.nb_i * BN + cg * 32;
+        if (vec_ok && cg * 32 < BN && col + 32 <= s.n) epi_res_issue(est, col, t);
+      } else if (!kGeglu && e.residual && t.row_ok) {
         // the residual row segment comes from HBM: start pulling it into L2 while the tile's MMAs are still running
         const __half* rp = e.residual + t.row * e.ldr + t.nb_i * BN;
-        for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN && t.nb_i * BN + c0 < s.n; c0 += 64)
+        for (int c0 = cg * 32; c0 < BN && t.nb_i * BN + c0 < s.n; c0 += 64)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c0));
       }
       mbar_wait(&tfull_bar[as], aph, 4);
@@ -252,15 +268,29 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
   }
   p.b_slot_bytes = ((s.bn * kBK * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes + p.b_slot_bytes;
-  const int budget = 224 * 1024 - kEpiStagingTotal;
+  const int out_n_h = a.epi.geglu ? s.n / 2 : s.n;
+  const bool out_tma_h = tapgemm_out_tma_ok(a.epi) && out_n_h >= 32 && !getenv("VGEN_TAPGEMM_DIRECT_STORE");
+  const bool res_tma_h = out_tma_h && !a.epi.geglu && a.epi.residual && (a.epi.ldr & 7) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a.epi.residual) & 15) == 0 && !getenv("VGEN_TAPGEMM_DIRECT_RESIDUAL");
+  p.staging_bytes = kEpiStagingTotal * (res_tma_h ? 2 : 1);
+  const int budget = 224 * 1024 - p.staging_bytes;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + kEpiStagingTotal + (2 * stages + 6) * 8 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + p.staging_bytes + (2 * stages + 10) * 8 + 1024;
   {
     const int out_n = a.epi.geglu ? s.n / 2 : s.n;
-    p.out_tma = (tapgemm_out_tma_ok(a.epi) && out_n >= 32 && !getenv("VGEN_TAPGEMM_DIRECT_STORE")) ? 1 : 0;
+    p.out_tma = out_tma_h ? 1 : 0;
+    p.res_tma = res_tma_h ? 1 : 0;
+    if (p.res_tma) {
+      const uint64_t ld = (uint64_t)a.epi.ldr * 2;
+      const uint64_t dims[4] = {(uint64_t)out_n, (uint64_t)s.d1, (uint64_t)s.d2, (uint64_t)s.d3};
+      const uint64_t strides[3] = {ld, ld * s.d1, ld * s.d1 * s.d2};
+      const uint32_t box[4] = {32, (uint32_t)s.box1, (uint32_t)s.box2, 1};
+      int rc = make_tmap_f16(&p.map_res, a.epi.residual, 4, dims, strides, box, 64);
+      if (rc) return rc;
+    }
     if (p.out_tma) {
       const uint64_t ld = (uint64_t)a.epi.ldo * 2;
       const uint64_t dims[4] = {(uint64_t)out_n, (uint64_t)s.d1, (uint64_t)s.d2, (uint64_t)s.d3};
