@@ -253,3 +253,70 @@ def test_lcm_scheduler_host_math():
     s.set_timesteps(8)
     assert s.timesteps.tolist() == lo.lcm_timesteps(8) and len(set(s.timesteps.tolist())) == 8
     assert torch.equal(s.scale_model_input(torch.ones(2)), torch.ones(2))
+
+
+def test_cfg_forward_batches_only_when_safe(monkeypatch):
+    """diffusion.cfg_forward (host logic): one batch-2b call for models that opt in and kwargs that can be stacked,
+    otherwise the reference's two calls; outputs are split back in (cond, uncond) order."""
+    from vgen_b200.diffusion import cfg_forward
+
+    class Fake:
+        cfg_batch = True
+
+        def __init__(self):
+            self.calls = []
+
+        def __call__(self, x, t=None, **kw):
+            self.calls.append((x.shape[0], sorted(kw), t.shape[0]))
+            return x * 2 + kw["y"].sum(dim=(1, 2)).view(-1, 1, 1, 1, 1)
+
+    x, t = torch.randn(1, 4, 2, 3, 3), torch.tensor([7])
+    kc, ku = {"y": torch.ones(1, 5, 8), "fps": torch.tensor([8])}, {"y": torch.zeros(1, 5, 8), "fps": torch.tensor([8])}
+    monkeypatch.setenv("VGEN_CFG_BATCH", "1")
+    m = Fake()
+    yo, uo = cfg_forward(m, x, t, [kc, ku])
+    assert m.calls == [(2, ["fps", "y"], 2)]
+    assert torch.equal(yo, x * 2 + 40) and torch.equal(uo, x * 2)
+    m = Fake()
+    cfg_forward(m, x, t, [kc, ku], by_keyword=True)            # GaussianDiffusion calls model(xt, t=t, **kw)
+    assert m.calls == [(2, ["fps", "y"], 2)]
+    m = Fake()
+    cfg_forward(m, x, t, [kc, dict(ku, extra=torch.zeros(1))])  # different key sets -> the reference's two calls
+    assert [c[0] for c in m.calls] == [1, 1]
+    m = Fake()
+    cfg_forward(m, x, t, [dict(kc, y=torch.ones(1, 6, 8)), ku])  # shapes that cannot be stacked
+    assert [c[0] for c in m.calls] == [1, 1]
+    monkeypatch.setenv("VGEN_CFG_BATCH", "0")
+    m = Fake()
+    cfg_forward(m, x, t, [kc, ku])
+    assert [c[0] for c in m.calls] == [1, 1]
+    m = Fake()
+    m.cfg_batch = False                                          # e.g. a reference model passed to our sampler
+    monkeypatch.setenv("VGEN_CFG_BATCH", "1")
+    cfg_forward(m, x, t, [kc, ku])
+    assert [c[0] for c in m.calls] == [1, 1]
+
+
+def test_fastdiv_multiply_shift_is_exact():
+    """Mirror of make_fastdiv / fd_div (vgen_b200/csrc/tapgemm.h): the tile-index decomposition of the persistent
+    kernels must be exact for every divisor and every 31-bit numerator it can meet."""
+    rng = np.random.default_rng(0)
+
+    def make(d):
+        if d == 1:
+            return 0, 0
+        lg = int(np.ceil(np.log2(d)))
+        while (1 << lg) < d:
+            lg += 1
+        while lg > 0 and (1 << (lg - 1)) >= d:
+            lg -= 1
+        p = 31 + lg
+        return ((1 << p) + d - 1) // d, p - 32
+
+    ds = list(range(1, 2000)) + [int(v) for v in rng.integers(2000, 1 << 20, 300)]
+    xs = np.concatenate([np.arange(0, 5000), rng.integers(0, 1 << 31, 4000), np.array([(1 << 31) - 1])]).astype(np.uint64)
+    for d in ds:
+        mul, shr = make(d)
+        assert mul < (1 << 32)
+        q = xs if d == 1 else ((xs * np.uint64(mul)) >> np.uint64(32)) >> np.uint64(shr)
+        assert np.array_equal(q, xs // np.uint64(d)), d
