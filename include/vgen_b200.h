@@ -65,6 +65,9 @@ int vgen_conv2d_3x3(const void* x, int64_t nimg, int64_t h, int64_t w_, int64_t 
  * replaces: nn.Conv3d in TemporalConvBlock_v2 util.py:1662-1680 */
 int vgen_tconv3(const void* x, int64_t f, int64_t hw, int64_t c, const void* w, int64_t n, void* out,
                 int64_t ldo, const vgen_epilogue* epi, void* stream);
+/* the same for `batch` videos stored back to back ([batch][f][hw][c]); frames of different videos never mix */
+int vgen_tconv3_batch(const void* x, int64_t batch, int64_t f, int64_t hw, int64_t c, const void* w, int64_t n,
+                      void* out, int64_t ldo, const vgen_epilogue* epi, void* stream);
 
 /* ---- normalisation (norm.cu; HBM-bound, fp32 statistics) ---------------------------------------- */
 /* GroupNorm(32 groups) over x[n][p][c] fp16 (statistics per sample n over p*c/32 values), optional

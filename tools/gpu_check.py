@@ -146,6 +146,22 @@ def group_tapgemm(impl="sm100"):
             report(f"[{impl}] tconv3 f{f_} hw{hw} c{c}->{n} res{int(res)}", rel_err(out, ref), 2e-3)
         run_case(f"tconv f{f_} hw{hw}", f)
 
+    def tconv_batch_case(b, f_, hw, c, n):
+        def f():
+            x = rnd(b, f_, hw, c).half()
+            wt = rnd(n, c, 3, scale=(3 * c) ** -0.5).half()
+            wp = wt.permute(0, 2, 1).reshape(n, 3 * c).contiguous()
+            bias = rnd(n)
+            r = rnd(b, f_, hw, n).half()
+            out = ops.tconv3(x, wp, bias=bias, residual=r)
+            per_video = torch.stack([ops.tconv3(x[i].contiguous(), wp, bias=bias, residual=r[i].contiguous()) for i in range(b)])
+            torch.cuda.synchronize()
+            report(f"[{impl}] tconv3 batched b{b} f{f_} hw{hw} c{c}->{n} == per video (frames of videos never mix)",
+                   float((out.float() - per_video.float()).abs().max()), 0.0)
+        run_case(f"tconv batch {b} {f_} {hw}", f)
+
+    tconv_batch_case(2, 4, 220, 128, 128)
+    tconv_batch_case(3, 16, 64, 64, 96)
     tconv_case(4, 256, 64, 64)
     tconv_case(8, 220, 128, 128, res=True)
     tconv_case(16, 32, 64, 96)

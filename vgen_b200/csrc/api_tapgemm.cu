@@ -158,11 +158,11 @@ int vgen_conv2d_3x3(const void* x, int64_t nimg, int64_t h, int64_t w_, int64_t 
   return finish_and_launch(&t, epi, stream);
 }
 
-int vgen_tconv3(const void* x, int64_t f, int64_t hw, int64_t c, const void* w, int64_t n, void* out, int64_t ldo,
-                const vgen_epilogue* epi, void* stream) {
+int vgen_tconv3_batch(const void* x, int64_t batch, int64_t f, int64_t hw, int64_t c, const void* w, int64_t n, void* out,
+                      int64_t ldo, const vgen_epilogue* epi, void* stream) {
   VG_REQUIRE(x && w && out, "vgen_tconv3: null pointer");
-  VG_REQUIRE(f >= 0 && hw > 0 && c > 0 && n > 0, "vgen_tconv3: bad shape");
-  if (f == 0) return 0;
+  VG_REQUIRE(batch >= 0 && f >= 0 && hw > 0 && c > 0 && n > 0, "vgen_tconv3: bad shape");
+  if (f == 0 || batch == 0) return 0;
   TapGemmArgs t{};
   t.a = reinterpret_cast<const __half*>(x);
   t.w = reinterpret_cast<const __half*>(w);
@@ -173,7 +173,7 @@ int vgen_tconv3(const void* x, int64_t f, int64_t hw, int64_t c, const void* w, 
   s.c = (int)c;
   s.d1 = (int)hw;
   s.d2 = (int)f;
-  s.d3 = 1;
+  s.d3 = (int)batch;  // videos: the frame taps are zero-padded by the TMA unit at each video's first / last frame
   s.box1 = (int)(hw < 128 ? hw : 128);
   s.box2 = 1;
   if (hw < 128) {  // small planes: put several frames in one tile
@@ -190,6 +190,11 @@ int vgen_tconv3(const void* x, int64_t f, int64_t hw, int64_t c, const void* w, 
   fill_epilogue(&t, out, ldo, epi);
   VG_REQUIRE(!t.epi.group_bias, "vgen_tconv3: group_bias not supported");
   return finish_and_launch(&t, epi, stream);
+}
+
+int vgen_tconv3(const void* x, int64_t f, int64_t hw, int64_t c, const void* w, int64_t n, void* out, int64_t ldo,
+                const vgen_epilogue* epi, void* stream) {
+  return vgen_tconv3_batch(x, 1, f, hw, c, w, n, out, ldo, epi, stream);
 }
 
 }  // extern "C"

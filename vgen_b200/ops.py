@@ -155,21 +155,23 @@ def conv2d_3x3(x, w, bias=None, group_bias=None, residual=None, out=None, bn=0, 
 
 
 def tconv3(x, w, bias=None, residual=None, out=None, bn=0):
-    """x [f, hw, c] fp16 -> [f, hw, n]; temporal 3-tap conv, zero padded; w [n, 3*c], k = kt*c + ci."""
+    """x [f, hw, c] (one video) or [b, f, hw, c] (videos back to back) fp16 -> same with n channels; temporal 3-tap
+    conv, zero padded at every video's first / last frame; w [n, 3*c], k = kt*c + ci."""
     _chk16(x, "x"), _chk16(w, "w")
-    if not x.is_contiguous() or x.dim() != 3:
-        raise _l.VgenError("tconv3: x must be contiguous [f,hw,c]")
-    f, hw, c = x.shape
+    if not x.is_contiguous() or x.dim() not in (3, 4):
+        raise _l.VgenError("tconv3: x must be contiguous [f,hw,c] or [b,f,hw,c]")
+    b = 1 if x.dim() == 3 else x.shape[0]
+    f, hw, c = x.shape[-3:]
     n = w.shape[0]
     if w.shape[1] != 3 * c or not w.is_contiguous():
         raise _l.VgenError(f"tconv3: weight {tuple(w.shape)} does not match c={c}")
     if out is None:
-        out = torch.empty(f, hw, n, device=x.device, dtype=torch.float16)
+        out = torch.empty(*x.shape[:-1], n, device=x.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
     e, keep = _epilogue(n, bias, None, residual, 1.0, False, bn)
-    rc = _run("tapgemm", 2.0 * f * hw * n * 3 * c, 2.0 * (f * hw * c + 3 * c * n + f * hw * n),
-              lambda: _l.load().vgen_tconv3(_p(x), f, hw, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()),
-              tag=f"tconv3 f{f} hw{hw} c{c} n{n}")
+    rc = _run("tapgemm", 2.0 * b * f * hw * n * 3 * c, 2.0 * (b * f * hw * c + 3 * c * n + b * f * hw * n),
+              lambda: _l.load().vgen_tconv3_batch(_p(x), b, f, hw, c, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()),
+              tag=f"tconv3 b{b} f{f} hw{hw} c{c} n{n}")
     _l.check(rc, "vgen_tconv3")
     return out
 

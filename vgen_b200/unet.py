@@ -233,12 +233,9 @@ class _UNetBase(SpecModule):
             q = f"{p}temopral_conv.{name}."
             g = ops.group_norm(t, W[q + "0.g"], W[q + "0.b"], 1e-5, True, n=b)
             last = i == len(names) - 1
-            out = torch.empty_like(hcur)
-            for bi in range(b):
-                gv = g.view(b, f, h * w, L.cout)[bi]
-                rv = hcur.view(b, f, h * w, L.cout)[bi] if last else None
-                ops.tconv3(gv, W[f"{q}{widx}.w"], bias=W[f"{q}{widx}.b"], residual=rv, out=out.view(b, f, h * w, L.cout)[bi])
-            t = out
+            # all videos of the batch in one launch (the frame taps are zero-padded per video)
+            t = ops.tconv3(g.view(b, f, h * w, L.cout), W[f"{q}{widx}.w"], bias=W[f"{q}{widx}.b"],
+                           residual=hcur.view(b, f, h * w, L.cout) if last else None).view(hcur.shape)
         return t
 
     def _self_attn_spatial(self, xn, W, p, heads, n, hw, inner):
