@@ -1,6 +1,7 @@
-"""B200-native UNetSD_T2VBase / UNetSD_I2VGen: same constructor arguments, state_dict keys and
-forward signature as the reference classes (tools/modules/unet/unet_t2v.py:19-277,
-unet_i2vgen.py:19-346), but the forward is a fixed-layout graph of libvgen_b200.so kernels.
+"""B200-native UNetSD_T2VBase / UNetSD_I2VGen / UNetSD_VideoLCM / UNetSD_SR600 / UNetSD_HiGen: same constructor
+arguments, state_dict keys and forward signatures as the reference classes (tools/modules/unet/unet_t2v.py:19-277,
+unet_i2vgen.py:19-346, unet_videolcm.py:188-760, unet_sr600.py:52-299, unet_higen.py:175-467), but the forward is a
+fixed-layout graph of libvgen_b200.so kernels.
 
 Design (not a port of the reference's module tree):
   * activations stay fp16 channels-last [(b f), h, w, C] for the whole forward; the reference's dozens
@@ -48,13 +49,6 @@ def _geglu_bn(n):
         if n % bn == 0:
             return bn
     raise ValueError(f"GEGLU width {n} is not a multiple of 64")
-
-
-class _Weights:
-    """Device-side packed weights of one model (built by _pack)."""
-
-    def __init__(self):
-        self.t = {}
 
 
 class _UNetBase(SpecModule):
