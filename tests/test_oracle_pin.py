@@ -59,3 +59,42 @@ def test_ddim_tables_against_reference_class():
     tab = vo.ddim_tables(vo.make_betas("cosine", 1000, True, cosine_s=0.008))
     for k, v in tab.items():
         assert torch.equal(v, getattr(d, k)), k
+
+
+def test_higen_motion_cond_per_frame_branch():
+    """get_motion_embedding with motion_cond.size(1) == f (no interpolation), unet_higen.py:393-394."""
+    from oracle.make_golden import build_variant
+    torch.set_grad_enabled(False)
+    ref = refload.load()
+    case = CASES["higen_tiny"]
+    m = build_variant(ref, "higen", case["ctor"]).eval()
+    sd = synth.state_dict(synth.spec_of(m), seed=79)
+    m.load_state_dict(sd, strict=True)
+    inp = make_inputs(case)
+    b, f = inp["x"].shape[0], inp["x"].shape[2]
+    mc = torch.tensor([[100 + 37 * i + 11 * j for j in range(f)] for i in range(b)], dtype=torch.long)
+    kw = dict(spat_prior=inp["spat_prior"], motion_cond=mc, appearance_cond=inp["appearance_cond"])
+    out = m(inp["x"], inp["t"], y=inp["y"], **kw)
+    assert _maxrel(vo.unet_higen_forward(sd, inp["x"], inp["t"], inp["y"], **kw), out) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["t2v", "videolcm"])
+def test_fps_condition_branch(kind):
+    """use_fps_condition=True adds fps_embedding(sinusoidal(fps)) to the time embedding (unet_t2v.py:246-249)."""
+    from oracle.make_golden import build_variant
+    torch.set_grad_enabled(False)
+    ref = refload.load()
+    case = CASES["t2v_tiny" if kind == "t2v" else "videolcm_tiny"]
+    ctor = dict(case["ctor"], use_fps_condition=True)
+    m = (ref.UNetSD_T2VBase(**ctor) if kind == "t2v" else build_variant(ref, "videolcm", ctor)).eval()
+    sd = synth.state_dict(synth.spec_of(m), seed=80)
+    m.load_state_dict(sd, strict=True)
+    inp = make_inputs(case)
+    fps = torch.tensor([8] * inp["x"].shape[0], dtype=torch.long)
+    out = m(inp["x"], inp["t"], y=inp["y"], fps=fps)
+    fn = vo.unet_t2v_forward if kind == "t2v" else vo.unet_videolcm_forward
+    assert _maxrel(fn(sd, inp["x"], inp["t"], inp["y"], fps=fps, use_fps_condition=True), out) < 2e-5
+    # and the product's parameter spec follows the flag
+    from vgen_b200 import arch
+    kk = dict(ctor, dim_mult=tuple(ctor["dim_mult"]), attn_scales=tuple(ctor["attn_scales"]))
+    assert arch.unet_spec(arch.unet_plan(kind, **kk)) == [(k, tuple(s)) for k, s in synth.spec_of(m)]
