@@ -156,9 +156,10 @@ int vgen_scale_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int6
 /* One fused DDIM update (diffusion_ddim.py:157-162 CFG mix, :194-196 v->x0 | :190-192 eps->x0, :230-240):
  *   out = u + g*(y-u) in fp16 (u NULL: out = y); x0; eps; xt <- c4*x0 + c5*eps (+ c6*noise).
  * coef7 = {sqrt_ab[t], sqrt(1-ab[t]), sqrt(1/ab[t]), sqrt(1/ab[t]-1), sqrt(ab_prev), sqrt(1-ab_prev-sigma^2),
- *          sigma*mask} as fp32 (the host keeps the fp64 tables; timestep/index math is bit-exact there). */
+ *          sigma*mask} as fp32 (the host keeps the fp64 tables; timestep/index math is bit-exact there).
+ * x0_out (may be NULL) receives the predicted x0, the second value ddim_sample returns (:241). */
 int vgen_ddim_step(float* xt, const void* y, const void* u, const float* noise, int64_t n, float guide_scale,
-                   const float* coef7, int mean_type_v, void* stream);
+                   const float* coef7, int mean_type_v, float* x0_out, void* stream);
 
 /* GaussianDiffusion (diffusion_gauss.py), the SR600 sampler pair -- sampler_gauss.cu.
  * out[b][n_per] = u + guide_scale*(y-u) in fp16 (:206-210) and stats[b][4] = {sum y, sum y^2, sum out, sum out^2}

@@ -55,11 +55,26 @@ CASES = {
 }
 
 
+# Full-size parity cases: the BASELINE configs' real architectures and latent shapes.
+# No golden file: truth = the (reference-pinned) oracle run in fp32 on the same GPU, tests/test_gpu_fullsize.py.
+FULL_CASES = {
+    "full_t2v": dict(kind="t2v", ctor=FULL_CTORS["full_t2v"][1], seed=21, b=1, f=8, h=32, w=32, ntok=77, t=[751]),
+    "full_i2vgen": dict(kind="i2vgen", ctor=FULL_CTORS["full_i2vgen"][1], seed=22, b=1, f=16, h=88, w=160, ntok=77, t=[981]),
+    "full_videolcm": dict(kind="videolcm", ctor=FULL_CTORS["full_videolcm"][1], seed=23, b=1, f=16, h=32, w=56, ntok=77, t=[759]),
+    "full_sr600": dict(kind="sr600", ctor=FULL_CTORS["full_sr600"][1], seed=24, b=1, f=4, h=90, w=160, ntok=77, t=[600]),
+    "full_higen_f1": dict(kind="higen", ctor=FULL_CTORS["full_higen"][1], seed=25, b=1, f=1, h=32, w=56, ntok=77, t=[981],
+                          spec="full_higen"),
+    "full_higen_f32": dict(kind="higen", ctor=FULL_CTORS["full_higen"][1], seed=25, b=1, f=32, h=32, w=56, ntok=77, t=[981],
+                           spec="full_higen"),
+    "full_vae": dict(kind="vae", ctor=FULL_CTORS["full_vae"][1], seed=26, n=2, h=88, w=160, z_scale=1.0 / 0.18215),
+}
+
+
 def make_inputs(case):
     """Deterministic inputs (numpy PCG64 keyed by tensor name, like the weights)."""
     s = case["seed"] + 1000
     if case["kind"] == "vae":
-        d = {"z": synth.tensor("z", (case["n"], 4, case["h"], case["w"]), 1.0, s)}
+        d = {"z": synth.tensor("z", (case["n"], 4, case["h"], case["w"]), case.get("z_scale", 1.0), s)}
         if case.get("encode"):
             e = case["encode"]
             d["img"] = synth.tensor("img", (e["n"], 3, e["H"], e["W"]), 0.5, s).clamp(-1, 1)

@@ -81,13 +81,13 @@ def ddim_steps(num_timesteps, ddim_timesteps):
 
 
 def ddim_sample_loop(noise, model, model_kwargs, betas, guide_scale, ddim_timesteps, eta=0.0, mean_type="v",
-                     autocast_cfg=False, trace=None):
+                     autocast_cfg=False, trace=None, max_steps=None):
     """diffusion_ddim.py:244-254 (loop), :209-241 (ddim_sample), :147-206 (p_mean_variance) for
     var_type fixed_small, mean_type v|eps, clamp/percentile/condition_fn None.
 
     model(xt, t, **kwargs) -> tensor shaped like xt.  With autocast_cfg the classifier-free mix is done
     in the model's output dtype (fp16 under the reference's autocast); table entries are cast to xt's
-    dtype exactly like _i() (:10-16)."""
+    dtype exactly like _i() (:10-16).  max_steps (test aid): stop after that many steps of the schedule."""
     T = len(betas)
     tab = ddim_tables(betas)
     stride = T // ddim_timesteps
@@ -97,7 +97,9 @@ def ddim_sample_loop(noise, model, model_kwargs, betas, guide_scale, ddim_timest
     def pick(name, t):
         return tab[name].to(xt.device)[t].view(b, *([1] * (xt.ndim - 1))).to(xt)
 
-    for step in ddim_steps(T, ddim_timesteps):
+    for n_done, step in enumerate(ddim_steps(T, ddim_timesteps)):
+        if max_steps is not None and n_done >= max_steps:
+            break
         t = torch.full((b,), int(step), dtype=torch.long, device=xt.device)
         if guide_scale is None:
             out = model(xt, t, **model_kwargs)

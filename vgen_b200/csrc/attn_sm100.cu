@@ -386,10 +386,10 @@ extern "C" int vgen_attention_d64(const void* q, const void* k, const void* v, v
   p.kv_batch_div = (int)kv_batch_div;
   p.scale_log2 = scale * 1.4426950408889634f;
   const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 22 * 8 + 16 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
+    attr_once.mark();
   }
   dim3 grid((unsigned)cdiv(lq, 2 * kTileQ), (unsigned)heads, (unsigned)batch);
   attn_sm100_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -241,10 +241,10 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
                                                           tok_stride_o, seq_stride_o, sl2);
     } else {
       const size_t smem = 4 * 3 * 32 * 72 * sizeof(__half);
-      static bool attr_done = false;
-      if (!attr_done) {
+      static PerDeviceOnce attr_once;
+      if (attr_once.need()) {
         VG_CUDA(cudaFuncSetAttribute(attn_temporal_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_once.mark();
       }
       attn_temporal_kernel<32><<<blocks, 128, smem, st>>>(qp, kp, vp, op, nseq, (int)heads, (int)L, tok_stride, seq_stride,
                                                           tok_stride_o, seq_stride_o, sl2);

@@ -39,7 +39,16 @@ int check_cuda(cudaError_t e, const char* what);
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
-int sm_count();
+int sm_count();            // of the CURRENT device (cached per device)
+int current_device();
+
+// "do this once per device" guard for per-device function attributes (cudaFuncSetAttribute is per device: a process that
+// drives a second GPU must set the > 48 KB dynamic shared memory opt-in there too).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool need() const { return ((done.load(std::memory_order_acquire) >> (current_device() & 63)) & 1ull) == 0; }
+  void mark() { done.fetch_or(1ull << (current_device() & 63), std::memory_order_release); }
+};
 extern std::atomic<long long> g_launches;  // kernels launched by this library (vgen_launch_count)
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

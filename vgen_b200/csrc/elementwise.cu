@@ -266,7 +266,8 @@ struct DdimCoef {
   float c[8];
 };
 __global__ void ddim_step_kernel(float* __restrict__ xt, const __half* __restrict__ y, const __half* __restrict__ u,
-                                 const float* __restrict__ noise, long n, float guide, int has_u, DdimCoef k, int mean_v) {
+                                 const float* __restrict__ noise, long n, float guide, int has_u, DdimCoef k, int mean_v,
+                                 float* __restrict__ x0_out) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float out;
@@ -288,6 +289,7 @@ __global__ void ddim_step_kernel(float* __restrict__ xt, const __half* __restric
   float r = k.c[4] * x0 + k.c[5] * eps;
   if (noise) r += k.c[6] * noise[idx];
   xt[idx] = r;
+  if (x0_out) x0_out[idx] = x0;
 }
 
 // ------------------------------------------------------------------ VAE posterior sample
@@ -447,7 +449,7 @@ int vgen_vae_sample(const void* moments, const float* noise, float* z, int64_t n
 }
 
 int vgen_ddim_step(float* xt, const void* y, const void* u, const float* noise, int64_t n, float guide_scale,
-                   const float* coef7, int mean_type_v, void* stream) {
+                   const float* coef7, int mean_type_v, float* x0_out, void* stream) {
   VG_REQUIRE(xt && y && coef7 && n >= 0, "vgen_ddim_step: bad arguments");
   if (n == 0) return 0;
   DdimCoef k;
@@ -455,7 +457,7 @@ int vgen_ddim_step(float* xt, const void* y, const void* u, const float* noise, 
   k.c[7] = 0.f;
   ddim_step_kernel<<<nblk(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       xt, reinterpret_cast<const __half*>(y), reinterpret_cast<const __half*>(u), noise, n, guide_scale, u != nullptr, k,
-      mean_type_v);
+      mean_type_v, x0_out);
   VG_LAUNCH_CHECK("ddim_step_kernel");
   return 0;
 }

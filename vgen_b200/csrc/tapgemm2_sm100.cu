@@ -296,11 +296,11 @@ int tapgemm_sm100_2cta_launch(const TapGemmArgs& a, cudaStream_t stream) {
     }
   }
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
+    attr_once.mark();
   }
   int clusters = sm_count() / 2;
   if (clusters > p.total_pair_tiles) clusters = p.total_pair_tiles;

@@ -301,11 +301,11 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
     }
   }
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
+    attr_once.mark();
   }
   int grid = sm_count();
   if (grid > s.total_tiles) grid = s.total_tiles;

@@ -141,16 +141,16 @@ class DiffusionDDIM(object):
     @torch.no_grad()
     def ddim_sample(self, xt, t, model, model_kwargs={}, clamp=None, percentile=None, condition_fn=None, guide_scale=None,
                     ddim_timesteps=20, eta=0.0):
-        """One DDIM step (diffusion_ddim.py:209-241); returns (x_{t-1}, None).  All batch entries share
-        the timestep (true for every caller on the sampling path)."""
+        """One DDIM step (diffusion_ddim.py:209-241); returns (x_{t-1}, x0) like the reference.  All batch entries
+        share the timestep (true for every caller on the sampling path)."""
         if clamp is not None or percentile is not None or condition_fn is not None:
             raise NotImplementedError("vgen_b200 DiffusionDDIM: clamp / percentile / condition_fn are not used by the "
                                       "supported inference configs")
         if self.var_type != "fixed_small" or self.mean_type not in ("v", "eps"):
             raise NotImplementedError("vgen_b200 DiffusionDDIM: only var_type fixed_small with mean_type v|eps")
-        return self._ddim_step(xt, int(t.flatten()[0]), t, model, model_kwargs, guide_scale, ddim_timesteps, eta)
+        return self._ddim_step(xt, int(t.flatten()[0]), t, model, model_kwargs, guide_scale, ddim_timesteps, eta, want_x0=True)
 
-    def _ddim_step(self, xt, step, t, model, model_kwargs, guide_scale, ddim_timesteps, eta):
+    def _ddim_step(self, xt, step, t, model, model_kwargs, guide_scale, ddim_timesteps, eta, want_x0=False):
         if self.var_type != "fixed_small" or self.mean_type not in ("v", "eps"):
             raise NotImplementedError("vgen_b200 DiffusionDDIM: only var_type fixed_small with mean_type v|eps")
         ts = self._scale_timesteps(t)
@@ -161,14 +161,18 @@ class DiffusionDDIM(object):
             assert isinstance(model_kwargs, list) and len(model_kwargs) == 2
             y_out, u_out = cfg_forward(model, xt, ts, model_kwargs)
         coef = self.step_coefficients(step, ddim_timesteps, eta)
-        noise = torch.randn_like(xt)  # the reference draws it even when eta == 0 (:237): keeps RNG streams aligned
+        # the reference draws the noise in xt's dtype even when eta == 0 (:237) -- keeps the device RNG stream aligned;
+        # the kernel reads fp32, so a non-fp32 draw is converted (never reinterpreted)
+        noise = torch.randn_like(xt)
         y16 = y_out if y_out.dtype == torch.float16 else y_out.to(torch.float16)
         u16 = None if u_out is None else (u_out if u_out.dtype == torch.float16 else u_out.to(torch.float16))
         xt = xt if (xt.dtype == torch.float32 and xt.is_contiguous()) else xt.float().contiguous()
         xt = xt.clone()
+        x0 = torch.empty_like(xt) if want_x0 else None
         ops.ddim_step_(xt, y16.contiguous(), None if u16 is None else u16.contiguous(), coef, guide_scale,
-                       mean_type_v=(self.mean_type == "v"), noise=noise if coef[6] != 0.0 else None)
-        return xt, None
+                       mean_type_v=(self.mean_type == "v"),
+                       noise=noise.float().contiguous() if coef[6] != 0.0 else None, x0_out=x0)
+        return xt, x0
 
     @torch.no_grad()
     def ddim_sample_loop(self, noise, model, model_kwargs={}, clamp=None, percentile=None, condition_fn=None,

@@ -206,11 +206,14 @@ _gn_ws = {}
 
 
 def _gn_workspace(device, n):
+    """Partial-statistics scratch of vgen_group_norm, one per (device, stream): two streams of one device must not
+    share it (the stats -> finalize -> apply launches of different calls would interleave)."""
     need = int(_l.load().vgen_group_norm_workspace_bytes(n))
-    ws = _gn_ws.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _gn_ws.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, device=device, dtype=torch.uint8)
-        _gn_ws[device] = ws
+        _gn_ws[key] = ws
     return ws
 
 
@@ -474,14 +477,26 @@ def adaptive_avgpool(x, oh, ow, silu_in=False):
     return y
 
 
-def ddim_step_(xt, y, u, coef7, guide_scale, mean_type_v=True, noise=None):
-    """In-place fused CFG + DDIM update of the fp32 latent xt; y/u fp16 model outputs (same layout)."""
-    if xt.dtype != torch.float32 or not xt.is_contiguous():
-        raise _l.VgenError("ddim_step_: xt must be contiguous fp32")
+def ddim_step_(xt, y, u, coef7, guide_scale, mean_type_v=True, noise=None, x0_out=None):
+    """In-place fused CFG + DDIM update of the fp32 latent xt; y/u fp16 model outputs (same layout).
+    x0_out (optional, fp32 like xt) receives the predicted x0 (diffusion_ddim.py:241 returns it)."""
+    if xt.dtype != torch.float32 or not xt.is_contiguous() or not xt.is_cuda:
+        raise _l.VgenError("ddim_step_: xt must be a contiguous CUDA fp32 tensor")
     _chk16(y, "y")
+    if not y.is_contiguous() or y.numel() != xt.numel():
+        raise _l.VgenError("ddim_step_: y must be contiguous with xt's element count")
+    if u is not None:
+        _chk16(u, "u")
+        if not u.is_contiguous() or u.numel() != xt.numel():
+            raise _l.VgenError("ddim_step_: u must be contiguous with xt's element count")
+    if noise is not None and (noise.dtype != torch.float32 or not noise.is_contiguous() or not noise.is_cuda
+                              or noise.numel() != xt.numel()):
+        raise _l.VgenError("ddim_step_: noise must be a contiguous CUDA fp32 tensor with xt's element count")
+    if x0_out is not None and (x0_out.dtype != torch.float32 or not x0_out.is_contiguous() or x0_out.numel() != xt.numel()):
+        raise _l.VgenError("ddim_step_: x0_out must be a contiguous fp32 tensor with xt's element count")
     c = (ctypes.c_float * 7)(*[float(v) for v in coef7])
     rc = _l.load().vgen_ddim_step(_p(xt), _p(y), _p(u), _p(noise), xt.numel(), float(guide_scale or 0.0), c,
-                                  1 if mean_type_v else 0, _stream())
+                                  1 if mean_type_v else 0, _p(x0_out), _stream())
     _l.check(rc, "vgen_ddim_step")
     return xt
 

@@ -14,6 +14,7 @@ below, which implements the same `build` contract: `cls(**{k: v for k != 'type'}
 """
 from __future__ import annotations
 
+import logging
 import warnings
 
 
@@ -71,12 +72,14 @@ def register(force_local: bool = False):
             from utils.registry_class import AUTO_ENCODER as A, DIFFUSION as D, MODEL as M  # the reference's singletons
             regs = (M, D, A)
             USING_REFERENCE_REGISTRY = True
-        except Exception:  # noqa: BLE001 - reference not on sys.path
+        except ImportError:  # the reference is not on sys.path: use the local mirror (tests, bench)
             regs = None
     if regs is None:
         regs = (MODEL or Registry("MODEL"), DIFFUSION or Registry("DIFFUSION"), AUTO_ENCODER or Registry("AUTO_ENCODER"))
         USING_REFERENCE_REGISTRY = False
     MODEL, DIFFUSION, AUTO_ENCODER = regs
+    logging.getLogger("vgen_b200").info("vgen_b200.register: using %s registries",
+                                        "the reference's (utils.registry_class)" if USING_REFERENCE_REGISTRY else "local mirror")
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # replacing the reference classes is the point
         for cls in (UNetSD_T2VBase, UNetSD_I2VGen, UNetSD_VideoLCM, UNetSD_SR600, UNetSD_HiGen):

@@ -71,6 +71,13 @@ class _UNetBase(SpecModule):
             raise NotImplementedError("vgen_b200: use_image_dataset (training-time flag) is not supported")
         if adapter_transformer_layers != 1:
             raise NotImplementedError("vgen_b200: adapter_transformer_layers != 1 is not supported")
+        # arguments that would change the reference's graph must not be swallowed silently (dropout / use_checkpoint /
+        # training / inpainting / p_all_* only matter for training and are accepted as no-ops)
+        if temporal_attn_times != 1:
+            raise NotImplementedError("vgen_b200: temporal_attn_times != 1 (extra TemporalTransformers per block) is not "
+                                      "used by any released config and is not supported")
+        if use_sim_mask:
+            raise NotImplementedError("vgen_b200: use_sim_mask=True (masked temporal attention) is not supported")
         self.plan = arch.unet_plan(self.KIND, in_dim=in_dim, dim=dim, y_dim=y_dim, context_dim=context_dim, out_dim=out_dim,
                                    num_tokens=num_tokens, dim_mult=tuple(dim_mult), num_heads=num_heads, head_dim=head_dim,
                                    num_res_blocks=num_res_blocks, attn_scales=tuple(attn_scales),
