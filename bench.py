@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- denoise-steps/s (and decoded frames/s) of the VGen sampling hot path on B200.
+"""bench.py -- denoise-steps/s (and decoded frames/s, videos/s) of the VGen sampling hot path on B200.
 
-Workload (BASELINE.json configs[1]): i2vgen_xl, 16 frames, 1280x704 (latent [1,4,16,88,160]), DDIM
-with classifier-free guidance (2 UNet forwards + 1 fused DDIM update per step), synthetic image + text
-conditioning, random-init weights of the real architecture (UNetSD_I2VGen, 1.42 B parameters).
-A "step" is one denoising step.  N GPUs run N independent trajectories (weak scaling), the only
-collective is the one-time NCCL weight broadcast.
+Headline workload (BASELINE.json configs[1], `--workload i2vgen`, the default): i2vgen_xl, 16 frames, 1280x704
+(latent [1,4,16,88,160]), DDIM with classifier-free guidance (2 UNet evaluations + 1 fused DDIM update per step),
+synthetic image + text conditioning, random-init weights of the real architecture (UNetSD_I2VGen, 1.42 B parameters).
+A "step" is one denoising step.  N GPUs run N independent trajectories (weak scaling); the only collective is the
+one-time NCCL broadcast of the packed fp16 weight arena.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload i2vgen|videolcm|sr600|higen]
 
-Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job steps/s with inputs
-resident in HBM; e2e = the same through the public DIFFUSION/MODEL API with HOST (pinned) buffers,
-H2D/D2H inside the timed region; roofline for the dominant kernel (tapgemm, tensor-bound); cpu_baseline =
-the oracle (CPU port of the reference) on a bounded sample.  `--impl reference` times that CPU oracle
-alone (the reference ships no CPU or Blackwell path of its own).
+The other workloads are BASELINE configs 3 / 4 / 5 driven the way the reference's engines drive them
+(inference_videolcm_entrance.py:171-255, inference_sr600_entrance.py:256-280, inference_higen_entrance.py:197-236):
+  videolcm  UNetSD_VideoLCM 16f 448x256, 4 LCM steps (no CFG) + 16-frame decode per prompt, one prompt per GPU
+  sr600     UNetSD_SR600 32f 1280x720: 30 DDIM-inversion steps + 30 DPM-Solver++(2M) SDE CFG steps + 32-frame decode
+  higen     UNetSD_HiGen 448x256: stage 1 (1 frame, 50 CFG DDIM steps) + stage 2 (32 frames, 50 CFG steps) + decode
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job steps/s with inputs resident in
+HBM; e2e = the same through the public DIFFUSION/MODEL API with HOST (pinned) buffers, H2D/D2H inside the timed
+region; roofline for the dominant kernel family (tapgemm, tensor-bound); cpu_baseline = the oracle (CPU port of the
+reference) on a bounded sample; gpu_eager_baseline = the oracle on THIS GPU under fp16 autocast (the reference's
+PyTorch-eager path with flash SDPA standing in for xformers -- the "beat this" number of SURVEY.md section 8d).
+`--impl reference` times the CPU oracle alone (the reference ships no CPU or Blackwell path of its own).
 """
 from __future__ import annotations
 
@@ -30,16 +38,35 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-WORKLOAD = "i2vgen_xl_16f_1280x704_ddim_cfg"
-FRAMES, LAT_H, LAT_W = 16, 88, 160
-STEP_TFLOP = 176.19        # one CFG denoise step = 2 x 88.095 TFLOP
-UNET_KW = dict(in_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
-               head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], dropout=0.1, temporal_attention=True,
-               temporal_attn_times=1, use_checkpoint=True, use_fps_condition=False, use_sim_mask=False, concat_dim=4)
+_FULL_UNET = dict(in_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
+                  head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], dropout=0.1, temporal_attention=True,
+                  temporal_attn_times=1, use_checkpoint=True, use_fps_condition=False, use_sim_mask=False)
 VAE_KW = dict(ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
                             ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0), embed_dim=4)
-DIFF_KW = dict(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
-               mean_type="v", var_type="fixed_small", loss_type="mse", noise_strength=0.1)
+DDIM_COSINE = dict(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+                   mean_type="v", var_type="fixed_small", loss_type="mse", noise_strength=0.1)
+DDIM_LINEAR_SD = dict(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085, last_beta=0.012,
+                                                                 zero_terminal_snr=True),
+                      mean_type="v", var_type="fixed_small", loss_type="mse", noise_strength=0.1)
+
+# Algorithmic work per denoise step, SURVEY.md section 8d (reference op count, FLOP = 2 MAC).
+WORKLOADS = {
+    "i2vgen": dict(name="i2vgen_xl_16f_1280x704_ddim_cfg", kind="i2vgen", cls="UNetSD_I2VGen", ctor=dict(_FULL_UNET, concat_dim=4),
+                   latent=(1, 4, 16, 88, 160), step_tflop=176.19, fwd_per_step=2, frame_hw=(704, 1280), decode_frames=16,
+                   decode_chunk=2, config="configs/i2vgen_xl_infer.yaml"),
+    "videolcm": dict(name="videolcm_t2v_16f_448x256_lcm4", kind="videolcm", cls="UNetSD_VideoLCM",
+                     ctor=dict(_FULL_UNET, concat_dim=8, num_tokens=4), latent=(1, 4, 16, 32, 56), step_tflop=8.667,
+                     fwd_per_step=1, frame_hw=(256, 448), decode_frames=16, decode_chunk=2,
+                     config="configs/videolcm_t2v_infer.yaml"),
+    "sr600": dict(name="tft2v_sr600_32f_1280x720_dpmpp2m_sde_cfg", kind="sr600", cls="UNetSD_SR600", ctor=dict(_FULL_UNET),
+                  latent=(1, 4, 32, 90, 160), step_tflop=2 * 185.3, fwd_per_step=2, frame_hw=(720, 1280), decode_frames=32,
+                  decode_chunk=4, config="configs/tft2v_32frames_sr600_infer.yaml"),
+    "higen": dict(name="higen_32f_448x256_stage2_ddim_cfg", kind="higen", cls="UNetSD_HiGen",
+                  ctor=dict(_FULL_UNET, context_embedding_depth=2, num_tokens=16), latent=(1, 4, 32, 32, 56),
+                  step_tflop=2 * 17.22, fwd_per_step=2, frame_hw=(256, 448), decode_frames=32, decode_chunk=2,
+                  config="configs/higen_infer.yaml"),
+}
+LCM_CONFIG = dict(video_compositions=["text"], resolution=[448, 256])
 
 
 def measured_peaks():
@@ -97,16 +124,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synth_conditioning(seed, device):
-    """SURVEY.md section 8d synthetic inputs (CPU generator, then moved)."""
+def synth_conditioning(wl, seed, device):
+    """SURVEY.md section 8d synthetic inputs (CPU generator, then moved): unit-scale text tokens etc."""
+    b, c, f, h, w = wl["latent"]
     g = torch.Generator().manual_seed(seed)
-    y = torch.randn(1, 77, 1024, generator=g)
-    y_neg = torch.randn(1, 77, 1024, generator=g)
-    image = torch.randn(1, 1, 1024, generator=g)
-    local = (0.18215 * torch.randn(1, 4, 1, LAT_H, LAT_W, generator=g)).repeat(1, 1, FRAMES, 1, 1)
-    noise = torch.randn(1, 4, FRAMES, LAT_H, LAT_W, generator=g)
-    fps = torch.tensor([16], dtype=torch.long)
-    host = dict(y=y, y_neg=y_neg, image=image, local_image=local.contiguous(), noise=noise, fps=fps)
+    host = dict(y=torch.randn(1, 77, 1024, generator=g), y_neg=torch.randn(1, 77, 1024, generator=g))
+    if wl["kind"] == "i2vgen":
+        host["image"] = torch.randn(1, 1, 1024, generator=g)
+        host["local_image"] = (0.18215 * torch.randn(1, 4, 1, h, w, generator=g)).repeat(1, 1, f, 1, 1).contiguous()
+        host["fps"] = torch.tensor([16], dtype=torch.long)
+    host["noise"] = torch.randn(1, 4, f, h, w, generator=g)
+    if wl["kind"] == "higen":   # inference_higen_entrance.py:197-229 (motion_factor 500, appearance_factor 1.0)
+        host["spat_noise"] = torch.randn(1, 4, 1, h, w, generator=g)
+        sim = torch.cat([torch.linspace(0.0, 1.0, f)[:-1], torch.linspace(1.0, 0.0, f)])
+        host["appearance"] = torch.stack([sim[i:i + f] for i in range(len(sim) - f, -1, -1)])[None].contiguous()
+        host["motion"] = torch.tensor([[500] * (f - 1)], dtype=torch.long)
     if device is None:
         return host
     return {k: v.to(device) for k, v in host.items()}
@@ -132,22 +164,37 @@ def usable_cpus():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU oracle timing (cpu_baseline and --impl reference)
-_CPU_CACHE = {}
-
-
-def _cpu_oracle_setup(threads):
-    """Full-size UNetSD_I2VGen weights for the CPU oracle (values are irrelevant for timing: a 16M-value
-    random base is tiled with per-tensor scales, generated in ~1 s instead of 15 s of randn), the sample
-    inputs, and the sample's algorithmic FLOPs counted on meta tensors."""
-    if _CPU_CACHE:
-        return _CPU_CACHE
-    from torch.utils.flop_counter import FlopCounterMode
-
+# oracle plumbing (cpu_baseline, --impl reference, gpu_eager_baseline): the ONLY places bench.py touches oracle/
+def _oracle_forward(kind):
     from oracle import vgen_oracle as vo
+    return {"i2vgen": vo.unet_i2vgen_forward, "videolcm": vo.unet_videolcm_forward, "sr600": vo.unet_sr600_forward,
+            "higen": vo.unet_higen_forward}[kind]
+
+
+def _oracle_kwargs(kind, c, f, neg=False):
+    """Keyword arguments of one oracle / model call from a conditioning dict (cond or uncond branch)."""
+    y = c["y_neg"] if neg else c["y"]
+    if kind == "i2vgen":
+        return dict(y=y, image=torch.zeros_like(c["image"]) if neg else c["image"], local_image=c["local_image"], fps=c["fps"])
+    if kind == "higen":
+        return dict(y=y, spat_prior=c["spat_prior"], motion_cond=c["motion"], appearance_cond=c["appearance"])
+    return dict(y=y)
+
+
+_CPU_CACHE = {}
+# latents the CPU sample may use, smallest first; the largest whose CFG step fits the budget is taken
+_CPU_LADDER = [(2, 16, 16), (4, 32, 32), (4, 48, 80), (8, 48, 80), (8, 88, 160), (16, 88, 160)]
+
+
+def _cpu_oracle_setup(wl_key, threads):
+    """Full-size weights for the CPU oracle (values are irrelevant for timing: a 16M-value random base is tiled with
+    per-tensor scales, generated in ~1 s instead of 15 s of randn)."""
+    if wl_key in _CPU_CACHE:
+        return _CPU_CACHE[wl_key]
     from vgen_b200 import arch
+    wl = WORKLOADS[wl_key]
     torch.set_num_threads(threads)
-    spec = arch.unet_spec(arch.unet_plan("i2vgen", **UNET_KW))
+    spec = arch.unet_spec(arch.unet_plan(wl["kind"], **wl["ctor"]))
     base = torch.randn(1 << 24, generator=torch.Generator().manual_seed(0))
     sd = {}
     off = 0
@@ -167,51 +214,91 @@ def _cpu_oracle_setup(threads):
             flat = flat + 1.0
         sd[name] = flat.reshape(shape).contiguous()
         off += n
-    f, h, w = 4, 32, 32
+    _CPU_CACHE[wl_key] = dict(sd=sd, spec=spec, flops={})
+    return _CPU_CACHE[wl_key]
+
+
+def _cpu_inputs(wl, f, h, w, device="cpu"):
     gi = torch.Generator().manual_seed(1)
+    c = dict(y=torch.randn(1, 77, 1024, generator=gi), y_neg=torch.randn(1, 77, 1024, generator=gi))
+    if wl["kind"] == "i2vgen":
+        c.update(image=torch.randn(1, 1, 1024, generator=gi), local_image=torch.randn(1, 4, f, h, w, generator=gi), fps=torch.tensor([16]))
+    if wl["kind"] == "higen":
+        c.update(spat_prior=torch.randn(1, 4, h, w, generator=gi), appearance=torch.rand(1, f, 32, generator=gi),
+                 motion=torch.full((1, max(f - 1, 1)), 500, dtype=torch.long) if f > 1 else torch.zeros(1, dtype=torch.long))
     x = torch.randn(1, 4, f, h, w, generator=gi)
-    kw = dict(y=torch.randn(1, 77, 1024, generator=gi), image=torch.randn(1, 1, 1024, generator=gi),
-              local_image=torch.randn(1, 4, f, h, w, generator=gi), fps=torch.tensor([16]))
-    msd = {n: torch.empty(s, device="meta") for n, s in spec}
-    mkw = {k: torch.empty(v.shape, device="meta", dtype=v.dtype) for k, v in kw.items()}
+    return x, {k: v.to(device) for k, v in c.items()}
+
+
+def _forward_flops(wl_key, f, h, w):
+    """Algorithmic FLOPs of one oracle forward at this latent, counted on meta tensors."""
+    from torch.utils.flop_counter import FlopCounterMode
+    c = _cpu_oracle_setup(wl_key, usable_cpus())
+    if (f, h, w) in c["flops"]:
+        return c["flops"][(f, h, w)]
+    wl = WORKLOADS[wl_key]
+    fwd = _oracle_forward(wl["kind"])
+    msd = {n: torch.empty(s, device="meta") for n, s in c["spec"]}
+    x, kw = _cpu_inputs(wl, f, h, w, "meta")
     with torch.no_grad(), FlopCounterMode(display=False) as fc:
-        vo.unet_i2vgen_forward(msd, torch.empty(x.shape, device="meta"), torch.empty(1, device="meta", dtype=torch.long), **mkw)
-    _CPU_CACHE.update(sd=sd, x=x, kw=kw, fwd_flops=float(fc.get_total_flops()), shape=(f, h, w), vo=vo)
-    return _CPU_CACHE
+        fwd(msd, torch.empty(x.shape, device="meta"), torch.empty(1, device="meta", dtype=torch.long), **_oracle_kwargs(wl["kind"], kw, f))
+    c["flops"][(f, h, w)] = float(fc.get_total_flops())
+    return c["flops"][(f, h, w)]
 
 
-def cpu_oracle_sample(budget_s=15.0, threads=None, max_reps=4):
-    """Time the oracle (CPU restatement of the reference, fp32, all usable host cores) on a bounded
-    sample of the workload: CFG denoise steps (2 UNet forwards each) of the SAME 1.42B-parameter
-    architecture at a reduced latent, scaled to the metric's unit by algorithmic FLOPs."""
+def cpu_oracle_sample(wl_key="i2vgen", budget_s=20.0, threads=None, max_reps=4, cpu_tflops_hint=None):
+    """Time the oracle (CPU restatement of the reference, fp32, all usable host cores) on a bounded sample of the
+    workload: CFG denoise steps of the SAME 1.4 B-parameter architecture at the LARGEST latent of a ladder whose step
+    fits the budget, scaled to the metric's unit by algorithmic FLOPs (the ratio to the full config is stated)."""
     threads = threads or usable_cpus()
-    c = _cpu_oracle_setup(threads)
-    vo, sd, x, kw = c["vo"], c["sd"], c["x"], c["kw"]
+    wl = WORKLOADS[wl_key]
+    c = _cpu_oracle_setup(wl_key, threads)
+    fwd = _oracle_forward(wl["kind"])
+    nf = wl["fwd_per_step"]
     t = torch.tensor([500])
+    full_f = wl["latent"][2]
+    # UNetSD_SR600's (2,1)-padded down / row-cropped up-sampling round-trips only for heights 8k+2 (unet_sr600.py:151-153)
+    ladder = [(min(f, full_f), h + 2 if wl["kind"] == "sr600" else h, w) for f, h, w in _CPU_LADDER
+              if h <= wl["latent"][3] and w <= wl["latent"][4]]
+    # probe the smallest latent to learn this host's throughput (counts as the warm-up), then pick the rung
+    f0, h0, w0 = ladder[0]
+    x, kw = _cpu_inputs(wl, f0, h0, w0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        fwd(c["sd"], x, t, **_oracle_kwargs(wl["kind"], kw, f0))
+        probe_s = time.perf_counter() - t0
+    rate = cpu_tflops_hint or (_forward_flops(wl_key, f0, h0, w0) / probe_s / 1e12)
+    pick = ladder[0]
+    for rung in ladder:
+        if nf * _forward_flops(wl_key, *rung) / 1e12 / max(rate, 1e-3) <= 0.6 * budget_s:
+            pick = rung
+    f, h, w = pick
+    x, kw = _cpu_inputs(wl, f, h, w)
+    flops = _forward_flops(wl_key, f, h, w)
     with torch.no_grad():
         t0 = time.perf_counter()
         n = 0
         while True:
-            vo.unet_i2vgen_forward(sd, x, t, **kw)
-            vo.unet_i2vgen_forward(sd, x, t, **kw)
+            for neg in ([False, True] if nf == 2 else [False]):
+                fwd(c["sd"], x, t, **_oracle_kwargs(wl["kind"], kw, f, neg))
             n += 1
             if time.perf_counter() - t0 > budget_s or n >= max_reps:
                 break
         dt = time.perf_counter() - t0
-    tflops = 2 * n * c["fwd_flops"] / dt / 1e12
-    f, h, w = c["shape"]
-    return {"value": tflops / STEP_TFLOP, "unit": "denoise-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{n} CFG step(s) (2 forwards each) of UNetSD_I2VGen, full 1.42B-param architecture, fp32 oracle, latent "
-                      f"[1,4,{f},{h},{w}] ({c['fwd_flops'] / 1e12:.3f} TFLOP/forward) in {dt:.1f}s = {tflops:.3f} TFLOP/s; "
-                      f"scaled to the {STEP_TFLOP} TFLOP/step workload",
-            "cpu_tflops": tflops}
+    tflops = nf * n * flops / dt / 1e12
+    ratio = nf * flops / 1e12 / wl["step_tflop"]
+    return {"value": tflops / wl["step_tflop"], "unit": "denoise-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{n} denoise step(s) ({nf} forward(s) each) of {wl['cls']}, full 1.4B-param architecture, fp32 oracle, latent "
+                      f"[1,4,{f},{h},{w}] ({flops / 1e12:.3f} TFLOP/forward = {ratio:.4f} of the {wl['step_tflop']} TFLOP step of "
+                      f"{wl['name']}) in {dt:.1f}s = {tflops:.3f} TFLOP/s; scaled to the full step by algorithmic FLOPs",
+            "cpu_tflops": tflops, "sample_latent": [1, 4, f, h, w], "sample_fraction_of_step": ratio}
 
 
-def cpu_oracle_sample_subprocess(budget_s=15.0, timeout_s=240):
+def cpu_oracle_sample_subprocess(wl_key, budget_s=20.0, timeout_s=300):
     """Run the CPU baseline in a child process with a hard timeout so it can never stall the bench."""
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample", str(budget_s)], capture_output=True,
-                           text=True, timeout=timeout_s)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample", str(budget_s), "--workload", wl_key],
+                           capture_output=True, text=True, timeout=timeout_s)
         for line in reversed(r.stdout.strip().splitlines()):
             if line.startswith("{"):
                 return json.loads(line)
@@ -223,26 +310,66 @@ def cpu_oracle_sample_subprocess(budget_s=15.0, timeout_s=240):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return 0
-    total_budget = 150.0
-    per = max(4.0, min(20.0, total_budget / max(1, args.steps + args.warmup)))
+    wl = WORKLOADS[args.workload]
+    total_budget = 170.0
+    per = max(4.0, min(30.0, total_budget / max(1, args.steps + args.warmup)))
+    hint = None
+    for _ in range(max(1, min(args.warmup, 2))):
+        hint = cpu_oracle_sample(args.workload, budget_s=per / 2, max_reps=1)["cpu_tflops"]
     vals = []
-    for _ in range(args.warmup):
-        cpu_oracle_sample(budget_s=per / 2, max_reps=1)
     t0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
-        last = cpu_oracle_sample(budget_s=per, max_reps=2)
+        last = cpu_oracle_sample(args.workload, budget_s=per, max_reps=2, cpu_tflops_hint=hint)
         vals.append(last["value"])
     dt = time.perf_counter() - t0
     v = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "denoise-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v if v > 0 else None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle (port of the reference's PyTorch path; the reference has no CPU/Blackwell path of its own)"},
+            "config": {"workload": wl["name"], "note": "CPU oracle (port of the reference's PyTorch path; the reference has no "
+                       "CPU/Blackwell path of its own); each step = a bounded sample at a reduced latent, FLOP-scaled",
+                       "sample_latent": last["sample_latent"], "sample_fraction_of_step": last["sample_fraction_of_step"]},
             "cpu_baseline": dict(last, value=v), "e2e": {"value": v, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": dt}
     print(json.dumps(line), flush=True)
     return 0
+
+
+def gpu_eager_baseline(wl_key, model, cond, dev, steps=2):
+    """The reference's PyTorch-eager GPU path on THIS GPU: the oracle (pinned to the reference) under
+    torch.autocast(fp16) -- cuBLAS / cuDNN / flash SDPA, fp32 master weights cast per op as autocast does -- for
+    `steps` denoise steps of the workload (same shapes, same weights).  An extra key, not the reference arm."""
+    wl = WORKLOADS[wl_key]
+    fwd = _oracle_forward(wl["kind"])
+    sd = {k: v for k, v in model.state_dict().items()}        # the module's own device-resident fp32 masters (no copy)
+    nf = wl["fwd_per_step"]
+    f = wl["latent"][2]
+    x = cond["noise"].clone()
+    t = torch.full((1,), 481, dtype=torch.long, device=dev)
+
+    def step():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            outs = [fwd(sd, x, t, **_oracle_kwargs(wl["kind"], cond, f, neg)) for neg in ([False, True] if nf == 2 else [False])]
+        return outs
+    try:
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            o = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": 1000.0 / ms, "unit": "denoise-steps/s", "ms_per_step": ms, "steps": steps, "finite": bool(torch.isfinite(o[0]).all()),
+                "what": f"oracle (reference restatement) on cuda under torch.autocast(fp16), {nf} forward(s)/step, flash SDPA, "
+                        f"torch {torch.__version__}; UNet forwards only (no sampler update)"}
+    except Exception as e:  # noqa: BLE001 - a comparator must never take the bench down
+        return {"error": repr(e)[:300]}
+    finally:
+        del sd
+        torch.cuda.empty_cache()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,7 +377,7 @@ def ncu_traffic(kernels):
     """DRAM bytes per launch of a kernel family, from the committed ncu launch list of this same command
     (profiles/<tag>_traffic.json, written by tools/ncu_summary.py); None when no capture is committed."""
     import glob
-    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_traffic.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
     if not files:
         return None
     try:
@@ -265,20 +392,149 @@ def ncu_traffic(kernels):
         return None
 
 
+def build_model(wl, registry, rank, dev):
+    """Random-init weights of the real architecture; every zero-initialised tensor (proj_out, ...) is randomised on
+    rank 0 so no branch multiplies by zero; the other ranks receive the packed arena over NCCL."""
+    torch.manual_seed(1234)
+    cfg = dict(type=wl["cls"], **wl["ctor"])
+    if wl["kind"] == "videolcm":
+        cfg["config"] = dict(LCM_CONFIG)
+    model = registry.build(cfg)
+    if rank == 0:
+        g = torch.Generator().manual_seed(4321)
+        for _, p in model.named_parameters():
+            if float(p.detach().abs().sum()) == 0.0:
+                p.data.normal_(0, 0.02, generator=g)
+    return model.to(dev).eval()
+
+
+def build_vae(registry, dev):
+    vae = registry.build(dict(type="AutoencoderKL", **VAE_KW))
+    gv = torch.Generator().manual_seed(99)
+    for p in vae.parameters():
+        if p.dim() > 1:
+            p.data.normal_(0, (p[0].numel()) ** -0.5, generator=gv)
+    return vae.to(dev).eval()
+
+
+def timed(fn, dev, parallel):
+    """CUDA-event time of fn() on the current stream (ms), max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    e0.record()
+    r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return parallel.max_over_ranks(e0.elapsed_time(e1), dev), r
+
+
+def decode_video(vae, lat, chunk):
+    """video_data = latents / scale_factor; chunks of decoder_bs frames through AutoencoderKL.decode
+    (inference_i2vgen_entrance.py:222-230)."""
+    z = (lat / 0.18215)[0].permute(1, 0, 2, 3).contiguous()
+    z = torch.nan_to_num(z).clamp(-10, 10)         # random-weight latents may blow up; values are irrelevant for timing
+    out = None
+    for i in range(0, z.shape[0], chunk):
+        out = vae.decode(z[i:i + chunk])
+    return out
+
+
+class Stepper:
+    """One denoise step of a workload through the public sampler classes, the way its engine calls them."""
+
+    def __init__(self, wl_key, model, dev, cond, DIFFUSION):
+        import vgen_b200
+        self.wl, self.k, self.model, self.dev, self.c = WORKLOADS[wl_key], wl_key, model, dev, cond
+        kind = self.wl["kind"]
+        f = self.wl["latent"][2]
+        if kind == "i2vgen":
+            self.diff = DIFFUSION.build(dict(type="DiffusionDDIM", **DDIM_COSINE))
+            self.kw = [_oracle_kwargs(kind, cond, f), _oracle_kwargs(kind, cond, f, True)]
+            self.steps = [int(s) for s in self.diff.ddim_steps(50)]
+        elif kind == "higen":
+            self.diff = DIFFUSION.build(dict(type="DiffusionDDIM", **DDIM_LINEAR_SD))
+            cond["spat_prior"] = torch.zeros(1, 4, *self.wl["latent"][3:], device=dev)
+            self.kw = [_oracle_kwargs(kind, cond, f), _oracle_kwargs(kind, cond, f, True)]
+            self.steps = [int(s) for s in self.diff.ddim_steps(50)]
+        elif kind == "videolcm":
+            self.sched = vgen_b200.LCMScheduler(prediction_type="v_prediction", beta_schedule="scaled_linear", clip_sample=False,
+                                                timestep_spacing="linspace", rescale_betas_zero_snr=True)
+            self.sched.set_timesteps(4, device=dev)
+            self.kw = _oracle_kwargs(kind, cond, f)
+        elif kind == "sr600":
+            self.diff = DIFFUSION.build(dict(
+                type="DiffusionDDIMSR",
+                reverse_diffusion=dict(schedule="cosine", mean_type="v", schedule_param=dict(num_timesteps=1000, zero_terminal_snr=True)),
+                forward_diffusion=dict(schedule="logsnr_cosine_interp", mean_type="v",
+                                       schedule_param=dict(num_timesteps=1000, zero_terminal_snr=True, scale_min=2.0, scale_max=4.0))))
+            self.kw = [_oracle_kwargs(kind, cond, f), _oracle_kwargs(kind, cond, f, True)]
+
+    def step(self, xt, i):
+        kind = self.wl["kind"]
+        if kind in ("i2vgen", "higen"):
+            s = self.steps[i % len(self.steps)]
+            t = torch.full((1,), s, dtype=torch.long, device=self.dev)
+            return self.diff._ddim_step(xt, s, t, self.model, self.kw, 9.0 if kind == "i2vgen" else 12.0, 50, 0.0)[0]
+        if kind == "videolcm":
+            if i % 4 == 0:
+                self.sched._step_index = None
+            t = self.sched.timesteps[i % 4]
+            out = self.model(self.sched.scale_model_input(xt, t), t.repeat(xt.size(0)).to(xt.dtype), t_w=None, **self.kw)
+            return self.sched.step(out, t, xt, return_dict=False)[0]
+        # sr600: one CFG denoise of the DPM-Solver++ loop (GaussianDiffusion.denoise at a fixed noise level, :163-247)
+        fd = self.diff.forward_diffusion
+        t = torch.full((1,), 400, dtype=torch.long, device=self.dev)
+        x0 = fd.denoise(xt, t, None, self.model, self.kw, guide_scale=9.0, guide_rescale=0.3)[-2]
+        return x0
+
+    def full_video(self, vae):
+        """One whole prompt the way the engine runs it (sampling + decode); returns (latent, frames)."""
+        kind, c, wl = self.wl["kind"], self.c, self.wl
+        if kind == "i2vgen":
+            lat = self.diff.ddim_sample_loop(c["noise"].clone(), self.model, self.kw, guide_scale=9.0, ddim_timesteps=50, eta=0.0)
+        elif kind == "videolcm":
+            self.sched.set_timesteps(4, device=self.dev)
+            lat = c["noise"].clone()
+            for t in self.sched.timesteps:
+                out = self.model(self.sched.scale_model_input(lat, t), t.repeat(1).to(lat.dtype), t_w=None, **self.kw)
+                lat = self.sched.step(out, t, lat, return_dict=False)[0]
+        elif kind == "sr600":
+            rev = self.diff.reverse_diffusion.ddim_reverse_sample_loop(x0=c["noise"] * 0.18215, model=self.model,
+                                                                      model_kwargs={"y": c["y_neg"]}, ddim_timesteps=30, reverse_steps=700)
+            lat = self.diff.forward_diffusion.sample(noise=rev, model=self.model, model_kwargs=self.kw, guide_scale=9.0,
+                                                     guide_rescale=0.3, solver="dpmpp_2m_sde", steps=30, t_max=699, t_min=0,
+                                                     discretization="trailing")
+        else:  # higen: spatial stage (1 frame) then temporal stage (32 frames)
+            f = wl["latent"][2]
+            spat_kw = [dict(y=c["y"], spat_prior=c["spat_prior"], motion_cond=torch.zeros(1, dtype=torch.long, device=self.dev),
+                            appearance_cond=torch.ones(1, 1, f, device=self.dev)),
+                       dict(y=c["y_neg"], spat_prior=c["spat_prior"], motion_cond=torch.zeros(1, dtype=torch.long, device=self.dev),
+                            appearance_cond=torch.ones(1, 1, f, device=self.dev))]
+            spat = self.diff.ddim_sample_loop(c["spat_noise"].clone(), self.model, spat_kw, guide_scale=12.0, ddim_timesteps=50, eta=0.0)
+            vae.decode((spat.squeeze(2) / 0.18215).clamp(-10, 10))
+            kw = [dict(k, spat_prior=torch.nan_to_num(spat.squeeze(2)).clamp(-10, 10)) for k in self.kw]
+            lat = self.diff.ddim_sample_loop(c["noise"].clone(), self.model, kw, guide_scale=12.0, ddim_timesteps=50, eta=0.0)
+        return lat, decode_video(vae, lat, wl["decode_chunk"])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="i2vgen", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--full-video", type=int, default=None, help="time one whole prompt (sampling + decode); default: on except i2vgen")
     ap.add_argument("--profile-pass", type=int, default=1, help="run one instrumented step for the roofline line")
     args = ap.parse_args()
 
     if args.cpu_sample is not None:
-        print(json.dumps(cpu_oracle_sample(budget_s=args.cpu_sample)), flush=True)
+        print(json.dumps(cpu_oracle_sample(args.workload, budget_s=args.cpu_sample)), flush=True)
         return 0
     from vgen_b200 import parallel
     if args.impl == "reference":
@@ -288,6 +544,7 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: vgen_b200 has no CPU path"}))
         return 1
+    wl = WORKLOADS[args.workload]
     rank, world, local_rank = parallel.init_from_env("nccl")
     if world != args.gpus and world > 1:
         args.gpus = world
@@ -295,36 +552,18 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     import vgen_b200
-    from vgen_b200 import lib, ops
+    from vgen_b200 import graph, lib, ops
     MODEL, DIFFUSION, AUTO_ENCODER = vgen_b200.register(force_local=True)
-    torch.manual_seed(1234)
-    model = MODEL.build(dict(type="UNetSD_I2VGen", **UNET_KW))
-    if rank != 0:  # only rank 0's weights matter: everyone else receives them over NCCL / NVLink
-        for p in model.parameters():
-            p.data.zero_()
-    # zero-initialised tensors (proj_out, ...) would make half the graph multiply by zero: randomise all
-    if rank == 0:
-        g = torch.Generator().manual_seed(4321)
-        for name, p in model.named_parameters():
-            if float(p.detach().abs().sum()) == 0.0:
-                p.data.normal_(0, 0.02, generator=g)
-    model = model.to(dev).eval()
-    bcast_bytes = parallel.broadcast_parameters(model, src=0)
-    diffusion = DIFFUSION.build(dict(type="DiffusionDDIM", **DIFF_KW))
-    c = synth_conditioning(8888 + rank, dev)
-    kw = [dict(y=c["y"], image=c["image"], local_image=c["local_image"], fps=c["fps"]),
-          dict(y=c["y_neg"], image=torch.zeros_like(c["image"]), local_image=c["local_image"], fps=c["fps"])]
-    ddim_T = 50
-    steps_all = diffusion.ddim_steps(ddim_T)
-
-    def one_step(xt, i):
-        step = int(steps_all[i % ddim_T])
-        t = torch.full((1,), step, dtype=torch.long, device=dev)
-        return diffusion._ddim_step(xt, step, t, model, kw, 9.0, ddim_T, 0.0)[0]
+    model = build_model(wl, MODEL, rank, dev)
+    # one-time weight distribution: the packed fp16 arena over NCCL / NVLink (timed on the device, untimed for the metric)
+    model.packed_tensors()
+    bc_ms, bcast_bytes = timed(lambda: parallel.broadcast_packed(model, src=0), dev, parallel)
+    c = synth_conditioning(wl, 8888 + rank, dev)
+    stepper = Stepper(args.workload, model, dev, c, DIFFUSION)
 
     xt = c["noise"].clone()
     for i in range(args.warmup):
-        xt = one_step(xt, i)
+        xt = stepper.step(xt, i)
     torch.cuda.synchronize()
     parallel.barrier()
 
@@ -335,84 +574,92 @@ def main():
         torch.cuda.synchronize()
         ev0.record()
         for i in range(args.steps):
-            xt = one_step(xt, args.warmup + i)
+            xt = stepper.step(xt, args.warmup + i)
         ev1.record()
         torch.cuda.synchronize()
-    launches = lib.launch_count() - l0
+    launches_eager = lib.launch_count() - l0
+    gstats = graph.stats(model)
     ms = ev0.elapsed_time(ev1)
     parallel.barrier()
     ms_max = parallel.max_over_ranks(ms, dev)
     finite = bool(torch.isfinite(xt).all())
 
     # ---- e2e: same step through the public API from HOST (pinned) buffers, H2D + D2H inside the timed region
-    host = synth_conditioning(8888 + rank, None)
+    host = synth_conditioning(wl, 8888 + rank, None)
+    cond_keys = [k for k in host if k not in ("noise", "spat_noise")]
     pinned = {k: v.pin_memory() for k, v in host.items()}
     xt_host = pinned["noise"].clone().pin_memory()
     out_host = torch.empty_like(xt_host).pin_memory()
-    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in ("y", "y_neg", "image", "local_image", "fps")) + xt_host.numel() * 4
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in cond_keys) + xt_host.numel() * 4
     d2h = out_host.numel() * 4
 
     def e2e_step(i):
-        d = {k: pinned[k].to(dev, non_blocking=True) for k in ("y", "y_neg", "image", "local_image", "fps")}
+        d = {k: pinned[k].to(dev, non_blocking=True) for k in cond_keys}
+        for k in c:
+            if k not in d:
+                d[k] = c[k]
         x = xt_host.to(dev, non_blocking=True)
-        kws = [dict(y=d["y"], image=d["image"], local_image=d["local_image"], fps=d["fps"]),
-               dict(y=d["y_neg"], image=torch.zeros_like(d["image"]), local_image=d["local_image"], fps=d["fps"])]
-        step = int(steps_all[i % ddim_T])
-        t = torch.full((1,), step, dtype=torch.long, device=dev)
-        x, _ = diffusion.ddim_sample(x, t, model, kws, guide_scale=9.0, ddim_timesteps=ddim_T, eta=0.0)
+        st = Stepper.__new__(Stepper)
+        st.__dict__.update(stepper.__dict__)
+        f = wl["latent"][2]
+        if isinstance(stepper.kw, list):
+            st.kw = [_oracle_kwargs(wl["kind"], d, f), _oracle_kwargs(wl["kind"], d, f, True)]
+        else:
+            st.kw = _oracle_kwargs(wl["kind"], d, f)
+        x = st.step(x, i)
         out_host.copy_(x, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        xt_host.copy_(out_host)
+        xt_host.copy_(torch.nan_to_num(out_host).clamp_(-1e4, 1e4))
 
     e2e_step(0)
-    torch.cuda.synchronize()
-    parallel.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     n_e2e = max(2, min(args.steps, 4))
-    for i in range(n_e2e):
-        e2e_step(1 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_ms, _ = timed(lambda: [e2e_step(1 + i) for i in range(n_e2e)], dev, parallel)
 
-    # ---- decode: AutoencoderKL.decode, 8 chunks x 2 frames (decoder_bs=2) of 1280x704
+    # ---- decode: AutoencoderKL.decode in chunks of decoder_bs frames
     decode = None
+    vae = None
     if not args.no_decode:
-        vae = AUTO_ENCODER.build(dict(type="AutoencoderKL", **VAE_KW))
-        gv = torch.Generator().manual_seed(99)
-        for p in vae.parameters():
-            if p.dim() > 1:
-                p.data.normal_(0, (p[0].numel()) ** -0.5, generator=gv)
-        vae = vae.to(dev).eval()
-        z = (xt / 0.18215)[0].permute(1, 0, 2, 3).contiguous()            # [16, 4, 88, 160]
-        z = torch.nan_to_num(z).clamp(-10, 10)
-        vae.decode(z[:2])
-        torch.cuda.synchronize()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record()
-        for i in range(0, FRAMES, 2):
-            img = vae.decode(z[i:i + 2])
-        d1.record()
-        torch.cuda.synchronize()
-        dms = parallel.max_over_ranks(d0.elapsed_time(d1), dev)
-        decode = {"frames_per_s": world * FRAMES / (dms / 1e3), "ms_per_16_frames": dms, "dtype": "f16 activations / f32 accumulate",
-                  "finite": bool(torch.isfinite(img).all())}
-        del vae, img
+        vae = build_vae(AUTO_ENCODER, dev)
+        decode_video(vae, xt[:, :, :2 * wl["decode_chunk"]], wl["decode_chunk"])     # warm-up + graph capture
+        nfr = min(wl["decode_frames"], xt.shape[2])
+        dms, img = timed(lambda: decode_video(vae, xt[:, :, :nfr], wl["decode_chunk"]), dev, parallel)
+        decode = {"frames_per_s": world * nfr / (dms / 1e3), "ms": dms, "frames": nfr, "frame_hw": list(wl["frame_hw"]),
+                  "chunk": wl["decode_chunk"], "dtype": "f16 activations / f32 accumulate", "finite": bool(torch.isfinite(img).all())}
+        del img
 
-    # ---- instrumented pass: per-kernel-family device time (CUDA events) for the roofline line
+    # ---- whole prompt (sampling + decode), the engines' end-to-end unit
+    full = None
+    want_full = args.full_video if args.full_video is not None else int(args.workload != "i2vgen")
+    if want_full and vae is not None:
+        if args.workload in ("videolcm",):
+            stepper.full_video(vae)                  # cheap: warm once so the timed prompt replays graphs
+        fms, (lat, frames) = timed(lambda: stepper.full_video(vae), dev, parallel)
+        nfr = wl["decode_frames"] + (1 if args.workload == "higen" else 0)
+        full = {"videos_per_s": world / (fms / 1e3), "s_per_video": fms / 1e3, "frames_per_s_e2e": world * nfr / (fms / 1e3),
+                "prompts": world, "finite": bool(torch.isfinite(lat).all()),
+                "what": {"i2vgen": "50 CFG DDIM steps + 16-frame decode", "videolcm": "4 LCM steps + 16-frame decode (8 chunks x 2)",
+                         "sr600": "30 DDIM-inversion steps + 30 DPM-Solver++(2M) SDE CFG steps + 32-frame decode",
+                         "higen": "stage 1: 50 CFG steps @1 frame + key-frame decode; stage 2: 50 CFG steps @32 frames + 32-frame decode"}[args.workload]}
+        del lat, frames
+    del vae
+    torch.cuda.empty_cache()
+
+    # ---- instrumented pass: per-kernel-family device time (CUDA events around every launch; graphs bypassed)
     roofline = None
     families = None
+    launches_step = None
     if args.profile_pass and rank == 0:
         ops.PROF = ops.KernelProfile()
-        xt2 = one_step(xt, 0)
+        l1 = lib.launch_count()
+        xt2 = stepper.step(xt, 0)
+        launches_step = lib.launch_count() - l1
         summ = ops.PROF.summary()
         shapes = ops.PROF.by_shape()
         ops.PROF = None
         try:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             rows = sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])
-            with open(os.path.join(ROOT, "gpurun_out", "prof_shapes.json"), "w") as fh:
+            with open(os.path.join(ROOT, "gpurun_out", f"prof_shapes_{args.workload}.json"), "w") as fh:
                 json.dump([{"op": k, "launches": v["launches"], "ms": round(v["ms"], 3),
                             "tflops": round(v["flops"] / 1e9 / max(v["ms"], 1e-9), 1), "gbs": round(v["bytes"] / 1e6 / max(v["ms"], 1e-9), 1)}
                            for k, v in rows], fh, indent=0)
@@ -429,27 +676,38 @@ def main():
                         "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
                         "launches_per_step": tg["launches"], "avg_launch_ms": tg["ms"] / tg["launches"],
                         "algorithmic_tflop_per_step": tg["flops"] / 1e12, "peak_source": pk["source"]}
-            tr = ncu_traffic(("tapgemm_sm100_2cta_kernel", "tapgemm_sm100_kernel"))
+            tr = ncu_traffic(("tapgemm_sm100_2cta_kernel", "tapgemm_sm100_kernel")) if args.workload == "i2vgen" else None
             if tr:
                 roofline["traffic"] = tr["bytes_per_launch"]
                 roofline["traffic_unit"] = "DRAM bytes / launch (dram__bytes_read.sum + dram__bytes_write.sum)"
                 roofline["traffic_source"] = tr["source"]
                 roofline["algorithmic_bytes_per_launch"] = tg["bytes"] / tg["launches"]
 
+    # kernels of OUR library executed inside the timed region: launches issued directly + graph replays x kernels per graph
+    replays = sum(v[1] for v in gstats.values())
+    launches = launches_eager
+    if launches_step is not None and replays:
+        launches = launches_step * args.steps       # every step replays the captured forward(s): same kernels as the eager step
     value = world * args.steps / (ms_max / 1e3)
     line = {"metric": "denoise_steps_per_s", "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "latent": [1, 4, FRAMES, LAT_H, LAT_W], "forwards_per_step": 2, "guide_scale": 9.0,
-                       "l2": "inputs larger than L2 (2.8 GB of weights + >100 MB activations stream per forward)",
+            "config": {"workload": wl["name"], "reference_config": wl["config"], "latent": list(wl["latent"]),
+                       "forwards_per_step": wl["fwd_per_step"], "cfg_batched": wl["fwd_per_step"] == 2,
+                       "l2": "inputs larger than L2 (2.8 GB of weights stream from HBM every forward)",
                        "parallelism": f"{world} independent trajectories (no data-path collective)",
-                       "weight_broadcast_bytes": bcast_bytes},
+                       "cuda_graph": {"enabled": graph.enabled(), "captures_replays": gstats,
+                                      "launches_issued_from_python_in_timed_region": launches_eager},
+                       "weight_broadcast": {"bytes": bcast_bytes, "ms": bc_ms, "what": "packed fp16 arena, NCCL, flat 256 MB buckets"}},
             "e2e": {"value": world * n_e2e / (e2e_ms / 1e3), "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary(), "finite": finite,
-            "tflops_effective": value * STEP_TFLOP / world, "decode": decode, "roofline": roofline, "kernel_families": families}
+            "tflops_effective": value * wl["step_tflop"] / world, "decode": decode, "full_video": full, "roofline": roofline,
+            "kernel_families": families}
+    if rank == 0 and not args.no_eager_baseline:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(args.workload, model, c, dev)
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_oracle_sample_subprocess(budget_s=15.0)
+            line["cpu_baseline"] = cpu_oracle_sample_subprocess(args.workload, budget_s=20.0)
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:

@@ -91,10 +91,13 @@ int vgen_attention_d64(const void* q, const void* k, const void* v, void* out, i
 /* Per-pixel attention over L <= 32 frames (attn_temporal.cu, register-resident mma.sync): token t of
  * sequence s lives at q + s*seq_stride + t*tok_stride (+ head*head_dim).  head_dim 64 is the fast path;
  * any head_dim <= 64, L <= 64 is served by a scalar kernel (I2VGen's 4-channel local encoder).
+ * Videos back to back in one launch: sequence s is pixel (s % seqs_per_batch) of video (s / seqs_per_batch), whose
+ * base is q + video*batch_stride (seqs_per_batch <= 0: one video, batch strides ignored).
  * replaces: memory_efficient_attention in TemporalTransformer util.py:1258-1261; Attention util.py:1396-1424 */
 int vgen_attention_temporal(const void* q, const void* k, const void* v, void* out, int64_t nseq, int64_t heads,
                             int64_t L, int64_t head_dim, int64_t tok_stride, int64_t seq_stride,
-                            int64_t tok_stride_o, int64_t seq_stride_o, float scale, void* stream);
+                            int64_t tok_stride_o, int64_t seq_stride_o, int64_t seqs_per_batch, int64_t batch_stride,
+                            int64_t batch_stride_o, float scale, void* stream);
 /* in-place softmax(x * scale) over rows of x[rows][n] fp16 (VAE AttnBlock, autoencoder.py:377-379) */
 int vgen_softmax_rows(void* x, int64_t rows, int64_t n, int64_t ld, float scale, void* stream);
 

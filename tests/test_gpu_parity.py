@@ -241,3 +241,34 @@ def test_cfg_batching_matches_two_forwards(golden_dir, monkeypatch):
     assert _rel_l2(a, b) < 2e-3
     truth = torch.from_numpy(gold["ddim_latent"]).cuda()
     assert _rel_l2(a, truth) < 1.5e-2
+
+
+@pytest.mark.parametrize("name", ["t2v_tiny_b2", "i2vgen_tiny", "higen_tiny", "vae_tiny"])
+def test_cuda_graph_replay_matches_eager(golden_dir, name, monkeypatch):
+    """the second call with one input signature is captured into a CUDA graph (static buffer
+    plan = the model's private pool); replays must reproduce the eager launch path bit for bit, follow NEW input
+    values (inputs are copied into the static buffers), and be dropped when the weights are repacked."""
+    from vgen_b200 import graph
+    case, m, inp, sdg, gold = _setup(golden_dir, name)
+    mine_fn, _ = _fns(case, m, inp, sdg)
+    monkeypatch.setenv("VGEN_CUDA_GRAPH", "0")
+    eager = mine_fn()
+    assert not graph.stats(m)
+    monkeypatch.setenv("VGEN_CUDA_GRAPH", "1")
+    outs = [mine_fn() for _ in range(4)]               # eager (first sighting), capture + replay, replay, replay
+    st = graph.stats(m)
+    key = "decode" if case["kind"] == "vae" else "forward"
+    assert st[key][0] == 1 and st[key][1] == 3, st
+    for o in outs:
+        assert torch.equal(o, eager)
+    # new values through the same graph
+    key_in = "z" if case["kind"] == "vae" else "x"
+    inp2 = dict(inp)
+    inp2[key_in] = inp[key_in] * 0.5 + 0.1
+    replayed = product_call(case, m, inp2)
+    monkeypatch.setenv("VGEN_CUDA_GRAPH", "0")
+    eager2 = product_call(case, m, inp2)
+    assert torch.equal(replayed, eager2) and not torch.equal(replayed, eager)
+    monkeypatch.setenv("VGEN_CUDA_GRAPH", "1")
+    m.load_state_dict({k: v * 1.01 for k, v in m.state_dict().items()}, strict=True)
+    assert not graph.stats(m), "repacking the weights must drop the captured graphs"

@@ -15,6 +15,7 @@ import collections
 import torch
 
 from . import arch, ops
+from .graph import graphed
 from .params import SpecModule
 from .unet import _f16, _f32, _pack_conv3x3
 
@@ -135,6 +136,7 @@ class AutoencoderKL(SpecModule):
         return out.view(n, h, w, c)
 
     # ------------------------------------------------------------------------------ public API
+    @graphed
     @torch.no_grad()
     def decode(self, z, **kwargs):
         """autoencoder.py:100-103 -> Decoder.forward :653-686.  z [n, 4, h, w] -> fp32 [n, 3, 8h, 8w]."""

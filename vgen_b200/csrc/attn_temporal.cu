@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __half* __rest
                                                             const __half* __restrict__ v, __half* __restrict__ out,
                                                             long nseq, int heads, int L, long tok_stride_q,
                                                             long seq_stride_q, long tok_stride_o, long seq_stride_o,
-                                                            float scale_log2) {
+                                                            float scale_log2, long spb, long batch_stride_q,
+                                                            long batch_stride_o) {
   constexpr int kRow = 72;  // halfs per smem row
   constexpr int MT = LP / 16;
   extern __shared__ __align__(16) __half sm_t[];
@@ -52,7 +53,9 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __half* __rest
   __half* sV = sK + LP * kRow;
 
   // ---- stage q/k/v rows of this (seq, head): each row is 128 contiguous bytes in HBM
-  const long base = seq * seq_stride_q + head * 64;
+  // videos back to back: sequence s is pixel (s % spb) of video (s / spb)
+  const long vid = seq / spb, pix = seq - vid * spb;
+  const long base = vid * batch_stride_q + pix * seq_stride_q + head * 64;
   for (int i = lane; i < LP * 8; i += 32) {
     const int t = i >> 3, piece = i & 7;
     uint4 uq = make_uint4(0, 0, 0, 0), uk = uq, uv = uq;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __half* __rest
       *reinterpret_cast<uint32_t*>(sQ + (m * 16 + g + 8) * kRow + col) = pack_half2(o[m][n][2] * inv_l[m][1], o[m][n][3] * inv_l[m][1]);
     }
   __syncwarp();
-  const long obase = seq * seq_stride_o + head * 64;
+  const long obase = vid * batch_stride_o + pix * seq_stride_o + head * 64;
   for (int i = lane; i < L * 8; i += 32) {
     const int t = i >> 3, piece = i & 7;
     *reinterpret_cast<uint4*>(out + obase + t * tok_stride_o + piece * 8) = *reinterpret_cast<const uint4*>(sQ + t * kRow + piece * 8);
@@ -185,13 +188,15 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __half* __rest
 // for the 4-channel local temporal encoder of UNetSD_I2VGen (unet_i2vgen.py:122-124, util.py:1396-1424).
 __global__ void attn_small_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
                                   __half* __restrict__ out, long nseq, int heads, int L, int d, long tok_stride,
-                                  long seq_stride, long tok_stride_o, long seq_stride_o, float scale) {
+                                  long seq_stride, long tok_stride_o, long seq_stride_o, float scale, long spb,
+                                  long batch_stride, long batch_stride_o) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nseq * heads * L) return;
   const int i = (int)(idx % L);
   const int head = (int)((idx / L) % heads);
   const long seq = idx / ((long)L * heads);
-  const long base = seq * seq_stride + head * d;
+  const long vid = seq / spb, pix = seq - vid * spb;
+  const long base = vid * batch_stride + pix * seq_stride + head * d;
   float qv[64];
   for (int c = 0; c < d; ++c) qv[c] = __half2float(q[base + i * tok_stride + c]);
   float mx = -INFINITY;
@@ -210,7 +215,7 @@ __global__ void attn_small_kernel(const __half* __restrict__ q, const __half* __
     l += e;
     for (int c = 0; c < d; ++c) acc[c] += e * __half2float(v[base + j * tok_stride + c]);
   }
-  const long ob = seq * seq_stride_o + head * d + i * tok_stride_o;
+  const long ob = vid * batch_stride_o + pix * seq_stride_o + head * d + i * tok_stride_o;
   for (int c = 0; c < d; ++c) out[ob + c] = __float2half_rn(acc[c] / l);
 }
 
@@ -220,9 +225,13 @@ using namespace vg;
 
 extern "C" int vgen_attention_temporal(const void* q, const void* k, const void* v, void* out, int64_t nseq, int64_t heads,
                                        int64_t L, int64_t head_dim, int64_t tok_stride, int64_t seq_stride,
-                                       int64_t tok_stride_o, int64_t seq_stride_o, float scale, void* stream) {
+                                       int64_t tok_stride_o, int64_t seq_stride_o, int64_t seqs_per_batch,
+                                       int64_t batch_stride, int64_t batch_stride_o, float scale, void* stream) {
   VG_REQUIRE(q && k && v && out, "vgen_attention_temporal: null pointer");
   VG_REQUIRE(nseq >= 0 && heads > 0 && L > 0 && head_dim > 0, "vgen_attention_temporal: bad shape");
+  if (seqs_per_batch <= 0) seqs_per_batch = nseq > 0 ? nseq : 1;
+  VG_REQUIRE(nseq % seqs_per_batch == 0, "vgen_attention_temporal: nseq must be a multiple of seqs_per_batch");
+  const long spb = seqs_per_batch;
   if (nseq == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __half *qp = reinterpret_cast<const __half*>(q), *kp = reinterpret_cast<const __half*>(k),
@@ -230,7 +239,8 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
   __half* op = reinterpret_cast<__half*>(out);
   const bool aligned = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                          reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
-                       tok_stride % 8 == 0 && seq_stride % 8 == 0 && tok_stride_o % 8 == 0 && seq_stride_o % 8 == 0;
+                       tok_stride % 8 == 0 && seq_stride % 8 == 0 && tok_stride_o % 8 == 0 && seq_stride_o % 8 == 0 &&
+                       batch_stride % 8 == 0 && batch_stride_o % 8 == 0;
   if (head_dim == 64 && L <= 32 && aligned) {
     const long items = nseq * heads;
     const unsigned blocks = (unsigned)((items + 3) / 4);
@@ -238,7 +248,7 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
     if (L <= 16) {
       const size_t smem = 4 * 3 * 16 * 72 * sizeof(__half);
       attn_temporal_kernel<16><<<blocks, 128, smem, st>>>(qp, kp, vp, op, nseq, (int)heads, (int)L, tok_stride, seq_stride,
-                                                          tok_stride_o, seq_stride_o, sl2);
+                                                          tok_stride_o, seq_stride_o, sl2, spb, batch_stride, batch_stride_o);
     } else {
       const size_t smem = 4 * 3 * 32 * 72 * sizeof(__half);
       static PerDeviceOnce attr_once;
@@ -247,7 +257,7 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
         attr_once.mark();
       }
       attn_temporal_kernel<32><<<blocks, 128, smem, st>>>(qp, kp, vp, op, nseq, (int)heads, (int)L, tok_stride, seq_stride,
-                                                          tok_stride_o, seq_stride_o, sl2);
+                                                          tok_stride_o, seq_stride_o, sl2, spb, batch_stride, batch_stride_o);
     }
     VG_LAUNCH_CHECK("attn_temporal_kernel");
     return 0;
@@ -255,7 +265,8 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
   VG_REQUIRE(head_dim <= 64 && L <= 64, "vgen_attention_temporal: unsupported (head_dim, L)");
   const long total = nseq * heads * L;
   attn_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(qp, kp, vp, op, nseq, (int)heads, (int)L, (int)head_dim,
-                                                                    tok_stride, seq_stride, tok_stride_o, seq_stride_o, scale);
+                                                                    tok_stride, seq_stride, tok_stride_o, seq_stride_o, scale, spb,
+                                                                    batch_stride, batch_stride_o);
   VG_LAUNCH_CHECK("attn_small_kernel");
   return 0;
 }

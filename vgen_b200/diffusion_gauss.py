@@ -163,8 +163,11 @@ class GaussianDiffusion(object):
         """:376-411 -> (x_{t+stride}, x0)."""
         if clamp is not None or percentile is not None:
             raise NotImplementedError("vgen_b200 GaussianDiffusion: clamp / percentile are not used on the sampling path")
-        xt = _f32c(xt)
-        step = self._uniform_step(t)
+        return self._ddim_reverse_step(_f32c(xt), self._uniform_step(t), t, model, model_kwargs, guide_scale, guide_rescale,
+                                       ddim_timesteps, reverse_steps)
+
+    def _ddim_reverse_step(self, xt, step, t, model, model_kwargs, guide_scale, guide_rescale, ddim_timesteps, reverse_steps):
+        """`step` is the host copy of the (batch-uniform) timestep: the loop never reads `t` back from the device."""
         stride = reverse_steps // ddim_timesteps
         x0 = self._predict_x0(xt, step, t, model, model_kwargs, guide_scale, guide_rescale)
         s = min(max(step + stride, 0), reverse_steps - 1)
@@ -179,12 +182,14 @@ class GaussianDiffusion(object):
     def ddim_reverse_sample_loop(self, x0, model, model_kwargs={}, clamp=None, percentile=None, guide_scale=None,
                                  guide_rescale=None, ddim_timesteps=20, reverse_steps=600):
         """:413-434."""
+        if clamp is not None or percentile is not None:
+            raise NotImplementedError("vgen_b200 GaussianDiffusion: clamp / percentile are not used on the sampling path")
         b = x0.size(0)
-        xt = x0
+        xt = _f32c(x0)
         for step in torch.arange(0, reverse_steps, reverse_steps // ddim_timesteps):
             t = torch.full((b,), int(step), dtype=torch.long, device=xt.device)
-            xt, _ = self.ddim_reverse_sample(xt, t, model, model_kwargs, clamp, percentile, guide_scale, guide_rescale,
-                                             ddim_timesteps, reverse_steps)
+            xt, _ = self._ddim_reverse_step(xt, int(step), t, model, model_kwargs, guide_scale, guide_rescale, ddim_timesteps,
+                                            reverse_steps)
         return xt
 
     # ---- DPM-Solver++(2M) SDE ---------------------------------------------------------------------

@@ -275,23 +275,33 @@ def attention_d64(q, k, v, heads, kv_batch_div=1, out=None):
 
 
 def attention_temporal(q, k, v, heads, head_dim, out=None):
-    """q/k/v [f, npix, heads*head_dim] views (frame-major): attention over the f tokens of each pixel."""
+    """q/k/v [f, npix, heads*head_dim] views (frame-major) of one video, or [b, f, npix, heads*head_dim] for b videos back
+    to back (one launch): attention over the f tokens of each pixel."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _chk16(t, nm)
-        if t.dim() != 3 or t.stride(2) != 1:
-            raise _l.VgenError(f"attention_temporal: {nm} must be [f, npix, c] with contiguous channels")
-    f, npix, inner = q.shape
+        if t.dim() not in (3, 4) or t.stride(-1) != 1:
+            raise _l.VgenError(f"attention_temporal: {nm} must be [(b,) f, npix, c] with contiguous channels")
+    if q.dim() == 3:
+        q, k, v = q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0)
+        out4 = None if out is None else out.unsqueeze(0)
+        squeeze = True
+    else:
+        out4, squeeze = out, False
+    b, f, npix, inner = q.shape
     if inner != heads * head_dim or k.shape != q.shape or v.shape != q.shape:
         raise _l.VgenError("attention_temporal: shape mismatch")
     if k.stride() != q.stride() or v.stride() != q.stride():
         raise _l.VgenError("attention_temporal: q/k/v must share strides")
-    if out is None:
-        out = torch.empty(f, npix, inner, device=q.device, dtype=torch.float16)
-    rc = _run("attention_temporal", 4.0 * npix * heads * f * f * head_dim, 2.0 * 4 * f * npix * inner,
-              lambda: _l.load().vgen_attention_temporal(_p(q), _p(k), _p(v), _p(out), npix, heads, f, head_dim, q.stride(0),
-                                                        q.stride(1), out.stride(0), out.stride(1), head_dim ** -0.5, _stream()))
+    if out4 is None:
+        out4 = torch.empty(b, f, npix, inner, device=q.device, dtype=torch.float16)
+    elif out4.shape != q.shape or out4.stride(-1) != 1:
+        raise _l.VgenError("attention_temporal: out must be shaped like q with contiguous channels")
+    rc = _run("attention_temporal", 4.0 * b * npix * heads * f * f * head_dim, 2.0 * 4 * b * f * npix * inner,
+              lambda: _l.load().vgen_attention_temporal(_p(q), _p(k), _p(v), _p(out4), b * npix, heads, f, head_dim, q.stride(1),
+                                                        q.stride(2), out4.stride(1), out4.stride(2), npix, q.stride(0),
+                                                        out4.stride(0), head_dim ** -0.5, _stream()))
     _l.check(rc, "vgen_attention_temporal")
-    return out
+    return out4[0] if squeeze else out4
 
 
 def attention_cross_small(q, k, v, heads, kv_batch_div=1, out=None):

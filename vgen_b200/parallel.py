@@ -79,6 +79,48 @@ def broadcast_parameters(module, src=0, bucket_bytes=256 << 20):
     return total
 
 
+@torch.no_grad()
+def broadcast_packed(module, src=0, bucket_bytes=256 << 20, offload_masters=False):
+    """Broadcast the PACKED weight arena of a vgen_b200 module (what its kernels read: fp16 GEMM matrices + fp32
+    bias / affine vectors, 2.84 GB for UNetSD_I2VGen instead of the 5.68 GB of fp32 masters) from rank `src` in flat
+    buckets over NCCL / NVLink.  Every rank packs its own (possibly meaningless) parameters first, which only fixes
+    the layout; the values then come from `src`.  With offload_masters the fp32 masters leave the device afterwards
+    (on ranks != src they are stale by construction: only inference through the packed arena is valid there).
+    Returns the number of bytes broadcast (0 without an initialised process group)."""
+    tensors = [t for _, t in module.packed_tensors()]
+    total = 0
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        by_dtype = {}
+        for t in tensors:
+            by_dtype.setdefault(t.dtype, []).append(t)
+        for dtype, ts in by_dtype.items():
+            bucket, size = [], 0
+
+            def flush():
+                nonlocal bucket, size, total
+                if not bucket:
+                    return
+                flat = torch.cat([t.reshape(-1) for t in bucket])
+                dist.broadcast(flat, src=src)
+                off = 0
+                for t in bucket:
+                    t.copy_(flat[off:off + t.numel()].view_as(t))
+                    off += t.numel()
+                total += flat.numel() * flat.element_size()
+                bucket, size = [], 0
+
+            for t in ts:
+                nbytes = t.numel() * t.element_size()
+                if bucket and size + nbytes > bucket_bytes:
+                    flush()
+                bucket.append(t)
+                size += nbytes
+            flush()
+    if offload_masters:
+        module.offload_masters()
+    return total
+
+
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

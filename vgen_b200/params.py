@@ -52,6 +52,7 @@ class SpecModule(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self._masters_offloaded = False
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
@@ -60,4 +61,27 @@ class SpecModule(nn.Module):
 
     @property
     def device(self):
+        if self._masters_offloaded and self._exec_device is not None:
+            return self._exec_device
         return next(self.parameters()).device
+
+    _masters_offloaded = False
+    _exec_device = None
+
+    def packed_tensors(self):
+        """(name, tensor) of the device-side packed weights (fp16 GEMM matrices, fp32 bias / affine vectors) in a
+        deterministic order -- what the forward actually reads; packs on first use."""
+        W = self._packed or self._pack()
+        return [(k, W[k]) for k in sorted(W) if torch.is_tensor(W[k])]
+
+    def offload_masters(self):
+        """Inference-only memory diet: keep just the packed fp16 arena on the device and move the fp32 master
+        parameters (reference key names; needed again only for state_dict() / re-packing) to host memory.
+        The packed weights and captured graphs stay valid; a later .to(device) / load_state_dict() re-packs."""
+        W = self._packed or self._pack()
+        self._exec_device = next(self.parameters()).device
+        for p in self.parameters():
+            p.data = p.data.to("cpu")
+        self._packed = W                      # .data assignment does not go through _apply: nothing was invalidated
+        self._masters_offloaded = True
+        return self

@@ -19,6 +19,7 @@ from __future__ import annotations
 import torch
 
 from . import arch, ops
+from .graph import graphed
 from .params import SpecModule
 
 
@@ -274,11 +275,8 @@ class _UNetBase(SpecModule):
 
     def _temporal_attn(self, xn, W, p, heads, b, f, hw, inner):
         qkv = ops.linear(xn, W[p + "qkv"]).view(b, f, hw, 3 * inner)
-        out = torch.empty(b, f, hw, inner, device=xn.device, dtype=torch.float16)
-        for bi in range(b):
-            v = qkv[bi]
-            ops.attention_temporal(v[:, :, :inner], v[:, :, inner:2 * inner], v[:, :, 2 * inner:], heads, 64, out=out[bi])
-        return out
+        # all videos of the batch in one launch
+        return ops.attention_temporal(qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:], heads, 64)
 
     def _temporal_transformer(self, x, L, W, b, f):
         """TemporalTransformer.forward, only_self_att=True (util.py:1240-1286): both attentions are
@@ -372,6 +370,7 @@ class UNetSD_T2VBase(_UNetBase):
     """Drop-in for tools/modules/unet/unet_t2v.py:19-20 (registered as MODEL 'UNetSD_T2VBase')."""
     KIND = "t2v"
 
+    @graphed
     @torch.no_grad()
     def forward(self, x, t, y=None, fps=None, masked=None, video_mask=None, focus_present_mask=None,
                 prob_focus_present=0., mask_last_frame_num=0, **kwargs):
@@ -419,10 +418,7 @@ class UNetSD_I2VGen(_UNetBase):
         tok = ximg.view(-1, cd)
         xn = ops.layer_norm(tok, W[e + "0.norm.g"], W[e + "0.norm.b"])
         qkv = ops.linear_small(xn, W[e + "0.fn.to_qkv.w"]).view(b, f, h * w, 6 * cd)
-        att = torch.empty(b, f, h * w, 2 * cd, device=dev, dtype=torch.float16)
-        for bi in range(b):
-            v = qkv[bi]
-            ops.attention_temporal(v[:, :, :2 * cd], v[:, :, 2 * cd:4 * cd], v[:, :, 4 * cd:], 2, cd, out=att[bi])
+        att = ops.attention_temporal(qkv[..., :2 * cd], qkv[..., 2 * cd:4 * cd], qkv[..., 4 * cd:], 2, cd)
         tok = ops.linear_small(att.view(-1, 2 * cd), W[e + "0.fn.to_out.0.w"], W[e + "0.fn.to_out.0.b"], residual=tok)
         hid = ops.linear_small(tok, W[e + "1.net.0.0.w"], W[e + "1.net.0.0.b"], gelu_out=True)
         tok = ops.linear_small(hid, W[e + "1.net.2.w"], W[e + "1.net.2.b"], residual=tok)
@@ -437,6 +433,7 @@ class UNetSD_I2VGen(_UNetBase):
         x = self._small_conv(x, W, "local_image_embedding.5.", stride=2, act_silu=True)
         return x.view(b, -1, x.shape[-1])
 
+    @graphed
     @torch.no_grad()
     def forward(self, x, t, y=None, image=None, local_image=None, masked=None, fps=None, video_mask=None,
                 focus_present_mask=None, prob_focus_present=0., mask_last_frame_num=0, **kwargs):
@@ -465,11 +462,12 @@ class UNetSD_I2VGen(_UNetBase):
             parts.append(ce.view(b, self.num_tokens, self.context_dim))
         ltot = sum(p.shape[1] for p in parts)
         ctx = torch.empty(b, ltot, self.context_dim, device=x.device, dtype=torch.float16)
-        off = 0
-        for part in parts:
-            for bi in range(b):
-                ops.copy2d(part[bi], ctx[bi, off:off + part.shape[1]])
-            off += part.shape[1]
+        off, cdim = 0, self.context_dim
+        ctx_rows = ctx.view(b, ltot * cdim)
+        for part in parts:                      # one strided copy per part (rows = videos)
+            lp = part.shape[1]
+            ops.copy2d(part.reshape(b, lp * cdim), ctx_rows[:, off * cdim:(off + lp) * cdim])
+            off += lp
         xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=c + cd).view(-1, c + cd)
         ops.copy2d(concat, xin[:, c:])
         out = self._trunk(xin.view(b * f, h, w, c + cd), emb, ctx, W, b, f)
@@ -492,6 +490,7 @@ class UNetSD_VideoLCM(_UNetBase):
         self.video_compositions = comps
         self.concat_dim = self.plan.concat_dim
 
+    @graphed
     @torch.no_grad()
     def forward(self, x, t, y=None, depth=None, image=None, motion=None, local_image=None, single_sketch=None,
                 masked=None, canny=None, sketch=None, histogram=None, fps=None, video_mask=None,
@@ -539,6 +538,7 @@ class UNetSD_SR600(_UNetBase):
         ops.fourier_lowfreq_filter(skip, self._SKIP_SCALE[n], out=o2[:, cx:])
         return out
 
+    @graphed
     @torch.no_grad()
     def forward(self, x, t, y, x_lr=None, fps=None, video_mask=None, focus_present_mask=None, prob_focus_present=0.,
                 mask_last_frame_num=0, **kwargs):
@@ -569,9 +569,8 @@ class UNetSD_HiGen(_UNetBase):
         p = "context_embedding."
         E, T = self.embed_dim, self.num_tokens
         yy = ops.linear(y16.view(-1, y16.shape[-1]), W[p + "input_mapping.w"], bias=W[p + "input_mapping.b"]).view(b, -1, E)
-        tok = torch.empty(b, T, E, device=y16.device, dtype=torch.float16)
-        for bi in range(b):
-            ops.copy2d(W[p + "tokens"], tok[bi])
+        tok = torch.empty(b, T * E, device=y16.device, dtype=torch.float16)
+        ops.copy2d(W[p + "tokens"].view(1, T * E).expand(b, T * E), tok)          # broadcast over the batch (row stride 0)
         tok = tok.view(b * T, E)
         heads = 8
         for d in range(self.plan.context_embedding_depth):
@@ -603,6 +602,7 @@ class UNetSD_HiGen(_UNetBase):
         ac = self._to_f16_rows(appearance_cond.reshape(b, f, -1))
         return ops.eltwise("add", emb, self._mlp(ac.view(b * f, -1), W, "asim_embedding."))
 
+    @graphed
     @torch.no_grad()
     def forward(self, x, t, y=None, fps=None, masked=None, video_mask=None, spat_prior=None, motion_cond=None,
                 appearance_cond=None, focus_present_mask=None, prob_focus_present=0., mask_last_frame_num=0, **kwargs):
@@ -617,9 +617,8 @@ class UNetSD_HiGen(_UNetBase):
         sp = ops.cp_to_pc(spat_prior.contiguous().float(), b, spat_prior.shape[1], h * w, c_pad=8).view(b, h, w, 8)
         img = self._conv3x3_any(sp, W, "img_embedding.").view(b, h * w, self.dim)
         img_rep = torch.empty(b, f, h * w, self.dim, device=x.device, dtype=torch.float16)
-        for bi in range(b):
-            for fi in range(f):
-                ops.copy2d(img[bi], img_rep[bi, fi])
+        for bi in range(b):                     # broadcast over the frames of a video (row stride 0): b launches, not b*f
+            ops.copy2d(img[bi].reshape(1, -1).expand(f, -1), img_rep[bi].view(f, -1))
         xin = ops.cp_to_pc(x.contiguous(), b, c, f * h * w, c_pad=8).view(b * f, h, w, 8)
         out = self._trunk(xin, emb, ctx, W, b, f, conv_in_residual=img_rep.view(-1, self.dim))
         return ops.pc_to_cp(out.view(b, f * h * w, self.out_dim), b, self.out_dim, f * h * w).view(b, self.out_dim, f, h, w)
