@@ -88,6 +88,11 @@ int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx
 int vgen_attention_d64(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
                        int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                        int64_t kv_batch_div, float scale, void* stream);
+/* Same op with an explicit q-tile stagger mode (0 / 1 / 2; the plain entry reads VGEN_ATTN_STAGGER once) and optional
+ * per-phase cycle counters of one CTA (timing16: 16 int64, may be NULL) -- tuning / diagnosis only (tools/bench_attn.py) */
+int vgen_attention_d64_debug(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
+                             int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                             int64_t kv_batch_div, float scale, int stagger, long long* timing16, void* stream);
 /* Per-pixel attention over L <= 32 frames (attn_temporal.cu, register-resident mma.sync): token t of
  * sequence s lives at q + s*seq_stride + t*tok_stride (+ head*head_dim).  head_dim 64 is the fast path;
  * any head_dim <= 64, L <= 64 is served by a scalar kernel (I2VGen's 4-channel local encoder).
@@ -178,6 +183,15 @@ int vgen_gauss_x0(const float* xt, const void* out, const double* stats, float g
  * scaling (:113), DPM-Solver++(2M) SDE update (:124-139), DDIM inversion step (:408-410) */
 int vgen_lincomb_f32(float* out, int64_t n, const float* x0, float a0, const float* x1, float a1, const float* x2,
                      float a2, const float* x3, float a3, void* stream);
+
+/* ---- video write-out ----------------------------------------------------------------------------- */
+/* utils/video_op.py:180-192 (save_i2vgen_video_safe; same arithmetic in save_t2vhigen_video_safe :276-288 and
+ * save_video_local :226-240): out[f][h][w][3] = uint8(trunc(clamp(video[c][f][h][w]*std[c] + mean[c], 0, 1) * 255)),
+ * i.e. mul_, add_, clamp_, *255, 'c f h w -> f h w c', numpy astype('uint8') -- bit-exact, on the device, so frames
+ * cross PCIe as bytes.  band_count (may be NULL; f entries, zeroed by the call) receives per frame the number of
+ * output bytes in [117, 137]: the last-frame anomaly test of :199-201 (ratio > 0.4 drops the frame). */
+int vgen_video_to_rgb8(const float* video, int64_t c, int64_t f, int64_t h, int64_t w, const float* mean3,
+                       const float* std3, uint8_t* out, unsigned long long* band_count, void* stream);
 
 #ifdef __cplusplus
 }

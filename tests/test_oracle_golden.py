@@ -118,3 +118,18 @@ def test_gauss_oracle_matches_reference_golden(golden_dir):
                                   gc["guide_scale"], gc["guide_rescale"], steps=gc["steps"], t_max=gc["noise_levels"] - 1,
                                   t_min=0, discretization="trailing")
     assert _maxrel(lat, torch.from_numpy(g["sample_latent"])) < 2e-4
+
+
+def test_video_oracle_matches_reference_frames(golden_dir):
+    """oracle/video_oracle.py vs the frames the REAL save_i2vgen_video_safe handed to its encoder
+    (tests/golden/video_out.npz, oracle/make_golden_video.py): bit-exact, including the dropped grey last frame."""
+    import numpy as np
+    from oracle import make_golden_video as mg, video_oracle as vo_
+    g = np.load(os.path.join(golden_dir, "video_out.npz"))
+    for name in mg.CASES:
+        v, mean, std = mg.make_video(name)
+        frames = vo_.drop_anomalous_last_frame(vo_.frames_uint8(v.numpy(), mean, std))
+        gold = g[name + "_frames"]
+        assert len(frames) == gold.shape[0], name
+        assert np.array_equal(np.stack(frames), gold), name
+    assert g["grey_last_frames"].shape[0] == int(g["grey_last_nframes_in"]) - 1

@@ -1,15 +1,30 @@
-"""Micro-benchmark of vgen_attention_d64 on the config-2 shapes (device time via CUDA events)."""
+"""Micro-benchmark of vgen_attention_d64 on the config-2 shapes (device time via CUDA events), for every q-tile stagger
+mode, plus the instrumented twin's per-phase cycle counters (softmax warp 0 of each q-tile of one mid-grid CTA)."""
+import ctypes
+import json
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-from vgen_b200 import ops  # noqa: E402
+from vgen_b200 import lib  # noqa: E402
+
+
+def call(q, k, v, out, h, div, stagger, timing=None):
+    L = lib.load()
+    b, lq, inner = q.shape
+    rc = L.vgen_attention_d64_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, h, lq, k.shape[1], q.stride(1),
+                                    k.stride(1), v.stride(1), out.stride(1), div, 64 ** -0.5, stagger,
+                                    timing.data_ptr() if timing is not None else None,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    lib.check(rc, "vgen_attention_d64_debug")
 
 
 def main():
     g = torch.Generator().manual_seed(0)
-    for (b, h, lq, lk, div) in [(16, 5, 14080, 14080, 1), (16, 10, 3520, 3520, 1), (16, 20, 880, 880, 1), (16, 5, 14080, 145, 16)]:
+    res = []
+    for (b, h, lq, lk, div) in [(32, 5, 14080, 14080, 1), (32, 10, 3520, 3520, 1), (32, 20, 880, 880, 1), (32, 20, 220, 220, 1),
+                                (32, 5, 14080, 145, 16), (32, 10, 3520, 145, 16)]:
         inner = h * 64
         if lq == lk and div == 1:
             qkv = torch.randn(b, lq, 3 * inner, generator=g).half().cuda()
@@ -18,22 +33,38 @@ def main():
             q = torch.randn(b, lq, inner, generator=g).half().cuda()
             kv = torch.randn(b // div, lk, 2 * inner, generator=g).half().cuda()
             k, v = kv[:, :, :inner], kv[:, :, inner:]
-        out = torch.empty(b, lq, inner, device="cuda", dtype=torch.float16)
-        fn = lambda: ops.attention_d64(q, k, v, h, kv_batch_div=div, out=out)  # noqa: E731
-        fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(5):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
+        outs = {}
+        for stagger in (0, 1, 2):
+            out = torch.empty(b, lq, inner, device="cuda", dtype=torch.float16)
+            fn = lambda: call(q, k, v, out, h, div, stagger)  # noqa: E731
             fn()
-            e.record()
             torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e))
-        ts.sort()
-        ms = ts[len(ts) // 2]
-        flops = 4.0 * b * h * lq * lk * 64
-        print({"shape": (b, h, lq, lk, div), "ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1)}, flush=True)
+            ts = []
+            for _ in range(7):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn()
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            ts.sort()
+            ms = ts[len(ts) // 2]
+            flops = 4.0 * b * h * lq * lk * 64
+            timing = torch.zeros(16, dtype=torch.int64, device="cuda")
+            call(q, k, v, out, h, div, stagger, timing)
+            torch.cuda.synchronize()
+            t = timing.cpu().tolist()
+            outs[stagger] = out.clone()
+            row = {"shape": (b, h, lq, lk, div), "stagger": stagger, "ms": round(ms, 4), "min_ms": round(ts[0], 4),
+                   "tflops": round(flops / ms / 1e9, 1),
+                   "phase_cycles_per_block": {f"tile{i}": {n: round(t[i * 8 + j] / max(t[i * 8 + 5], 1), 1)
+                                                          for j, n in enumerate(["wait_S", "ld_max", "wait_Pbuf", "exp_store", "total"])}
+                                              for i in (0, 1)}}
+            print(json.dumps(row), flush=True)
+            res.append(row)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "stagger must not change results"
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/bench_attn.json", "w"), indent=0)
 
 
 if __name__ == "__main__":

@@ -25,6 +25,8 @@
 // fp16 holds, so O can accumulate in TMEM across key blocks (tcgen05.mma accumulate) without a per-block
 // read-modify-write; on the rare advance the thread rescales its O row in TMEM (tcgen05.ld / st).  The final
 // O / l is exact: every term of row r carries the same 2^-m_ref factor.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -50,9 +52,12 @@ struct alignas(64) AttnParams {
   int lq, lk, heads;
   int kv_batch_div;   // kv batch index = batch / kv_batch_div (context shared by the frames of a video)
   float scale_log2;   // softmax scale * log2(e)
+  int stagger;        // 0: both q-tiles start together; 1 / 2: q-tile 1 starts half / one exponential phase after q-tile 0
+  long long* timing;  // kTiming only: per-phase cycle counters of one CTA's two softmax warps (tools/bench_attn.py)
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __grid_constant__ AttnParams p) {
+template <bool kTiming>
+__device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 2 x 16 KB
@@ -69,7 +74,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
   uint64_t* p_full = bars + 11;       // [2][2] per q-tile and P buffer: P(j) in smem, S(j) consumed, O rescaled
   uint64_t* o_full = bars + 15;       // [2][2] per q-tile and P buffer: PV(j) finished (buffer j&1 free, O readable)
   uint64_t* s_free = bars + 19;       // [2] per q-tile: S(j) is in registers, QK(j+1) may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* stag = bars + 21;         // [1] q-tile 0 is halfway through the exponentials of its first block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   // (one barrier per P buffer: the softmax warps may publish P(j+1) before the MMA warp has looked at P(j), and a
   // single barrier two phases ahead of its observer aliases)
 
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       mbar_init(&o_full[2 * i + 1], 1);
       mbar_init(&s_free[i], 4);
     }
+    mbar_init(stag, 4);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -162,6 +169,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       __syncwarp();
     };
     mbar_wait(q_full, 0, 11);
+    // Stagger: the two tiles' softmax warps share each SM sub-partition's MUFU pipe; started together they run their
+    // TMEM-load / max / publish phases at the same time and leave the pipe idle then.  Offsetting tile 1 by a fraction of
+    // an exponential phase makes one tile's bookkeeping overlap the other's exponentials (the offset is self-preserving:
+    // nothing later re-synchronises the tiles).
+    if (i == 1 && p.stagger == 1) mbar_wait(stag, 0, 17);
+    if (i == 1 && p.stagger == 2) mbar_wait(&p_full[0], 0, 18);   // a second observer of tile 0's first publish
     issue_qk(0);
     for (int j = 0; j < nkv; ++j) {
       if (j + 1 < nkv) {
@@ -201,10 +214,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
 
     float m_ref = -INFINITY;  // reference max (raw score units) all of this row's exponentials are relative to
     float l_run = 0.f;
+    long long tm_wait_s = 0, tm_ldmax = 0, tm_wait_p = 0, tm_exp = 0, tm_c0 = 0, tm_c1 = 0, tm_start = 0;
+    if (kTiming) tm_start = clock64();
 
     for (int j = 0; j < nkv; ++j) {
+      if (kTiming) tm_c0 = clock64();
       mbar_wait(&s_full[i], j & 1, 20);
       tc_fence_after();
+      if (kTiming) { tm_c1 = clock64(); tm_wait_s += tm_c1 - tm_c0; }
       const int valid = p.lk - j * kTileK;  // keys valid in this block (>= 128 unless last)
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld32(t_s + 0, s0);
@@ -273,8 +290,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[i]);
+      if (kTiming) { tm_c0 = clock64(); tm_ldmax += tm_c0 - tm_c1; }
       // P buffer j&1 was last read by PV(j-2)
       if (j >= 2) mbar_wait(&o_full[2 * i + (j & 1)], ((j >> 1) - 1) & 1, 23);
+      if (kTiming) { tm_c1 = clock64(); tm_wait_p += tm_c1 - tm_c0; }
       const uint32_t prow = prow0 + (j & 1) * kPBytes;
       const float neg_ms = -m_ref * sl2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
@@ -295,6 +314,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
   }
       VG_ATTN_EMIT(s0, 0, l0)
       VG_ATTN_EMIT(s1, 32, l1)
+      if (i == 0 && j == 0 && p.stagger == 1) {   // let tile 1 start now (uniform branch; never taken again)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stag);
+      }
       VG_ATTN_EMIT(s2, 64, l2)
       VG_ATTN_EMIT(s3, 96, l3)
 #undef VG_ATTN_EMIT
@@ -304,6 +327,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[2 * i + (j & 1)]);
+      if (kTiming) tm_exp += clock64() - tm_c1;
+    }
+    if (kTiming && p.timing && q == 0 && lane == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
+      long long* t = p.timing + i * 8;
+      t[0] = tm_wait_s, t[1] = tm_ldmax, t[2] = tm_wait_p, t[3] = tm_exp, t[4] = clock64() - tm_start, t[5] = nkv;
     }
     // ---- output: O / l
     mbar_wait(&o_full[2 * i + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1, 22);
@@ -339,13 +367,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
   }
 }
 
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __grid_constant__ AttnParams p) {
+  attn_sm100_body<false>(p);
+}
+// instrumented twin (phase cycle counters); only tools/bench_attn.py launches it (vgen_attention_d64_debug)
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_timing_kernel(const __grid_constant__ AttnParams p) {
+  attn_sm100_body<true>(p);
+}
+
 }  // namespace vg
 
 using namespace vg;
 
-extern "C" int vgen_attention_d64(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
-                                  int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                                  int64_t kv_batch_div, float scale, void* stream) {
+static int g_attn_stagger = -1;   // -1: read VGEN_ATTN_STAGGER once (default below)
+
+static int attention_d64_impl(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
+                              int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                              int64_t kv_batch_div, float scale, void* stream, int stagger, long long* timing) {
   VG_REQUIRE(q && k && v && out, "vgen_attention_d64: null pointer");
   VG_REQUIRE(batch >= 0 && heads > 0 && lq > 0 && lk > 0 && kv_batch_div >= 1 && batch % kv_batch_div == 0,
              "vgen_attention_d64: bad shape");
@@ -385,14 +423,40 @@ extern "C" int vgen_attention_d64(const void* q, const void* k, const void* v, v
   p.heads = (int)heads;
   p.kv_batch_div = (int)kv_batch_div;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 22 * 8 + 16 + 1024;
+  if (stagger < 0) {
+    if (g_attn_stagger < 0) {
+      const char* e = getenv("VGEN_ATTN_STAGGER");
+      g_attn_stagger = e ? atoi(e) : 0;
+    }
+    stagger = g_attn_stagger;
+  }
+  p.stagger = (lk > kTileK) ? stagger : 0;     // a single key block has nothing to overlap with
+  p.timing = timing;
+  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 23 * 8 + 16 + 1024;
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(attn_sm100_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.mark();
   }
   dim3 grid((unsigned)cdiv(lq, 2 * kTileQ), (unsigned)heads, (unsigned)batch);
-  attn_sm100_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (timing) attn_sm100_timing_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else attn_sm100_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   VG_LAUNCH_CHECK("attn_sm100_kernel");
   return 0;
+}
+
+extern "C" int vgen_attention_d64(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
+                                  int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                  int64_t kv_batch_div, float scale, void* stream) {
+  return attention_d64_impl(q, k, v, out, batch, heads, lq, lk, ldq, ldk, ldv, ldo, kv_batch_div, scale, stream, -1, nullptr);
+}
+
+// Tuning / diagnosis entry (tools/bench_attn.py): explicit stagger mode, optional phase counters (16 int64:
+// per q-tile {wait S, load+max, wait P buffer, exponentials+store, total, blocks, -, -}).
+extern "C" int vgen_attention_d64_debug(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
+                                        int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                        int64_t kv_batch_div, float scale, int stagger, long long* timing16, void* stream) {
+  return attention_d64_impl(q, k, v, out, batch, heads, lq, lk, ldq, ldk, ldv, ldo, kv_batch_div, scale, stream, stagger,
+                            timing16);
 }

@@ -371,7 +371,7 @@ int vgen_upsample_nearest2x(const void* x, void* y, int64_t nimg, int64_t h, int
 }
 
 int vgen_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, void* stream) {
-  VG_REQUIRE(src && dst && rows >= 0 && cols > 0 && lds >= cols && ldd >= cols, "vgen_copy2d: bad arguments");
+  VG_REQUIRE(src && dst && rows >= 0 && cols > 0 && (lds >= cols || lds == 0) && ldd >= cols, "vgen_copy2d: bad arguments");
   if (rows == 0) return 0;
   const bool vec = (cols % 8 == 0) && (lds % 8 == 0) && (ldd % 8 == 0) &&
                    (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);

@@ -19,6 +19,8 @@
 //   gn_finalize grid (N): one warp per group merges the partials with Chan's formula (robust to
 //               mean >> std) -> (mean, rstd).
 //   gn_apply    same thread->channel ownership, scale/shift in registers: y = silu?(x*scale + shift).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -170,6 +172,18 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float2* __restr
 // x * sigmoid(x); the quotient uses the approximate reciprocal (<= 1 ulp, the result is rounded to fp16): the
 // IEEE division sequence (~10 instructions) made gn_apply issue-bound (ncu r01k: 65% issue, 67% XU at 3.5 TB/s)
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// Variant with the reciprocal on the FMA pipe: gn_apply sits at 67 % of the XU (MUFU) pipe with two MUFU per element
+// (ex2 + rcp) while the FMA pipe is at 33 %.  1 / d for d = 1 + 2^t in [1, 2^126]: exponent-negation estimate (10 %),
+// three Newton steps (1.5e-7) = 6 FMA-pipe + 1 ALU instructions instead of one MUFU.
+__device__ __forceinline__ float silu_fma(float v) {
+  const float t = fminf(v * -1.4426950408889634f, 126.0f);
+  const float d = 1.0f + fast_exp2(t);
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  return v * r;
+}
 
 __device__ __forceinline__ uint4 norm8(const uint4& u, const float (&sc)[8], const float (&sh)[8], int silu) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&u);
@@ -180,7 +194,10 @@ __device__ __forceinline__ uint4 norm8(const uint4& u, const float (&sc)[8], con
     f[2 * k] = fmaf(t.x, sc[2 * k], sh[2 * k]);
     f[2 * k + 1] = fmaf(t.y, sc[2 * k + 1], sh[2 * k + 1]);
   }
-  if (silu) {
+  if (silu == 2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = silu_fma(f[k]);
+  } else if (silu) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
   }
@@ -482,6 +499,12 @@ int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, con
   GnGeom g;
   int rc = gn_geometry(n, p, (int)c, &g);
   if (rc) return rc;
+  static int silu_mode = -1;   // VGEN_GN_SILU: 1 = MUFU reciprocal, 2 = FMA-pipe reciprocal (tuning knob, read once)
+  if (silu_mode < 0) {
+    const char* e = getenv("VGEN_GN_SILU");
+    silu_mode = e ? atoi(e) : 1;
+  }
+  if (silu) silu = silu_mode == 2 ? 2 : 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float2* part = reinterpret_cast<float2*>(workspace);
   float2* stats = part + (long)n * kMaxSplits * kGroups;

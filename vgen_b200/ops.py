@@ -567,3 +567,19 @@ def vae_sample(moments, noise, scale):
     rc = _l.load().vgen_vae_sample(_p(moments), _p(noise), _p(z), n, zc, p, float(scale), _stream())
     _l.check(rc, "vgen_vae_sample")
     return z
+
+
+def video_to_rgb8(video, mean, std, want_band=True):
+    """video fp32 [3, f, h, w] (one batch entry, contiguous, CUDA) -> (uint8 [f, h, w, 3], per-frame count of bytes in
+    [117, 137] or None).  mean / std: 3 floats each (cfg.mean / cfg.std)."""
+    if video.dtype != torch.float32 or not video.is_cuda or not video.is_contiguous() or video.dim() != 4 or video.shape[0] != 3:
+        raise _l.VgenError("video_to_rgb8: video must be a contiguous CUDA fp32 tensor [3, f, h, w]")
+    c, f, h, w = video.shape
+    out = torch.empty(f, h, w, 3, device=video.device, dtype=torch.uint8)
+    band = torch.empty(f, device=video.device, dtype=torch.int64) if want_band else None
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    rc = _run("video_out", 0.0, 5.0 * video.numel(),
+              lambda: _l.load().vgen_video_to_rgb8(_p(video), c, f, h, w, m3, s3, _p(out), _p(band), _stream()))
+    _l.check(rc, "vgen_video_to_rgb8")
+    return out, band
