@@ -34,7 +34,7 @@ def main():
             kv = torch.randn(b // div, lk, 2 * inner, generator=g).half().cuda()
             k, v = kv[:, :, :inner], kv[:, :, inner:]
         outs = {}
-        for stagger in (0, 1, 2):
+        for stagger in (0, 3):
             out = torch.empty(b, lq, inner, device="cuda", dtype=torch.float16)
             fn = lambda: call(q, k, v, out, h, div, stagger)  # noqa: E731
             fn()
@@ -62,7 +62,7 @@ def main():
                                               for i in (0, 1)}}
             print(json.dumps(row), flush=True)
             res.append(row)
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "stagger must not change results"
+        assert torch.equal(outs[0], outs[3]), "stagger must not change results"
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_attn.json", "w"), indent=0)
 

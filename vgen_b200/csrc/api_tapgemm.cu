@@ -9,19 +9,29 @@ namespace vg {
 
 static int g_tapgemm_impl = 0;  // 0 = auto (CTA pairs when there are >= 2 M-tiles), 1 = simt, 2 = 1-CTA tcgen05, 3 = 2-CTA tcgen05
 
-static int pick_bn(long n, int geglu) {
+// N tile.  With many M tiles the cost is the padded N extent plus a per-tile constant (~24 columns' worth of
+// epilogue / pipeline fill).  With FEW M tiles (the 11x20 / 22x40 levels of the UNet, every layer of the 448x256
+// configs) the persistent grid runs ceil(tiles / CTA pairs) waves and the widest tile leaves most of the last wave
+// idle -- e.g. 32 row pairs x 1280 columns: BN 256 -> 160 tiles = 3 waves of 74 pairs (72 % busy), BN 160 -> 256
+// tiles = 4 waves at 0.66 of the per-wave time.  So the cost is waves x (BN + overhead), waves counted on this device.
+static int pick_bn(long n, int geglu, long m_pair_tiles, int clusters) {
   if (geglu) {
     for (int bn = 256; bn >= 64; bn -= 64)
       if (n % bn == 0) return bn;
     return 0;
   }
   if (n <= 96) return (int)((n + 31) / 32) * 32;
+  if (clusters < 1) clusters = 1;
   int best = 128;
   double best_cost = 1e30;
   for (int bn = 256; bn >= 96; bn -= 32) {
     const long nb = (n + bn - 1) / bn;
-    const double cost = (double)nb * bn * (1.0 + 24.0 / bn);
-    if (cost < best_cost) {
+    const long tiles = nb * (m_pair_tiles > 0 ? m_pair_tiles : 1);
+    const long waves = (tiles + clusters - 1) / clusters;
+    // many waves: the tail wave is amortised, fall back to total padded work
+    const double work = tiles > 8L * clusters ? (double)tiles / clusters : (double)waves;
+    const double cost = work * (bn + 24.0);
+    if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;
     }
@@ -74,7 +84,8 @@ static int finish_and_launch(TapGemmArgs* t, const vgen_epilogue* epi, void* str
   }
   TapGemmShape& s = t->shape;
   s.kc = s.c / 64;
-  int bn = (epi && epi->bn > 0) ? epi->bn : pick_bn(s.n, t->epi.geglu);
+  const long m_tiles_all = (long)s.d3 * cdiv(s.d2, s.box2) * cdiv(s.d1, s.box1);
+  int bn = (epi && epi->bn > 0) ? epi->bn : pick_bn(s.n, t->epi.geglu, (m_tiles_all + 1) / 2, sm_count() / 2);
   VG_REQUIRE(bn > 0, "tapgemm: no valid N tile (GEGLU needs n % 64 == 0)");
   s.bn = bn;
   s.nb = cdiv(s.n, bn);

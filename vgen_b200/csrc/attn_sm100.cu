@@ -75,7 +75,8 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
   uint64_t* o_full = bars + 15;       // [2][2] per q-tile and P buffer: PV(j) finished (buffer j&1 free, O readable)
   uint64_t* s_free = bars + 19;       // [2] per q-tile: S(j) is in registers, QK(j+1) may overwrite it
   uint64_t* stag = bars + 21;         // [1] q-tile 0 is halfway through the exponentials of its first block
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* turn = bars + 22;         // [2] stagger mode 3: the other q-tile has finished the exponentials of a block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   // (one barrier per P buffer: the softmax warps may publish P(j+1) before the MMA warp has looked at P(j), and a
   // single barrier two phases ahead of its observer aliases)
 
@@ -104,6 +105,8 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
       mbar_init(&s_free[i], 4);
     }
     mbar_init(stag, 4);
+    mbar_init(&turn[0], 4);
+    mbar_init(&turn[1], 4);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -293,6 +296,14 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
       if (kTiming) { tm_c0 = clock64(); tm_ldmax += tm_c0 - tm_c1; }
       // P buffer j&1 was last read by PV(j-2)
       if (j >= 2) mbar_wait(&o_full[2 * i + (j & 1)], ((j >> 1) - 1) & 1, 23);
+      // stagger mode 3: strict alternation of the two tiles' exponential phases (A0 B0 A1 B1 ...).  Both tiles share each
+      // sub-partition's MUFU pipe; run together they also run their TMEM-load / max / barrier phases together and the pipe
+      // idles then (measured: 2 x 2000 cycles of shared exponentials + 780 idle per block).  Taking turns, one tile's
+      // bookkeeping hides under the other's exponentials, which then have the pipe to themselves.
+      if (p.stagger == 3) {
+        if (i == 0) { if (j > 0) mbar_wait(&turn[0], (j - 1) & 1, 24); }
+        else mbar_wait(&turn[1], j & 1, 25);
+      }
       if (kTiming) { tm_c1 = clock64(); tm_wait_p += tm_c1 - tm_c0; }
       const uint32_t prow = prow0 + (j & 1) * kPBytes;
       const float neg_ms = -m_ref * sl2;
@@ -327,6 +338,7 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[2 * i + (j & 1)]);
+      if (p.stagger == 3 && lane == 0) mbar_arrive(&turn[1 - i]);
       if (kTiming) tm_exp += clock64() - tm_c1;
     }
     if (kTiming && p.timing && q == 0 && lane == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
@@ -432,7 +444,7 @@ static int attention_d64_impl(const void* q, const void* k, const void* v, void*
   }
   p.stagger = (lk > kTileK) ? stagger : 0;     // a single key block has nothing to overlap with
   p.timing = timing;
-  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 23 * 8 + 16 + 1024;
+  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 25 * 8 + 16 + 1024;
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
