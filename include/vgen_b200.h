@@ -88,11 +88,18 @@ int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx
 int vgen_attention_d64(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
                        int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                        int64_t kv_batch_div, float scale, void* stream);
-/* Same op with an explicit q-tile stagger mode (0 / 1 / 2; the plain entry reads VGEN_ATTN_STAGGER once) and optional
- * per-phase cycle counters of one CTA (timing16: 16 int64, may be NULL) -- tuning / diagnosis only (tools/bench_attn.py) */
+/* Single-head attention with head_dim 512 (attn_d512_sm100.cu, tcgen05 flash attention: the [lq, lk] score matrix
+ * never leaves the SM): out[b][i][:] = softmax_j(q[b][i].k[b][j] * scale) v[b][j][:]; q/k/v/out rows of 512 fp16 with
+ * row strides ld* (multiples of 8), batches lq*ld / lk*ld apart.
+ * replaces: AttnBlock.forward of the SD VAE, autoencoder.py:365-389 (w_ = bmm(q,k) * c**-0.5; softmax; bmm(v, w_)) */
+int vgen_attention_d512(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t lq, int64_t lk,
+                        int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, void* stream);
+/* Same op through the instrumented twin kernel: per-phase cycle counters of one mid-grid CTA's softmax warps
+ * (timing16: 16 int64: per q-tile {wait S, load+max, wait P buffer, exponentials+store, total, blocks}) -- diagnosis only
+ * (tools/bench_attn.py; the numbers behind DESIGN.md's account of where the attention kernel's time goes) */
 int vgen_attention_d64_debug(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
                              int64_t lq, int64_t lk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                             int64_t kv_batch_div, float scale, int stagger, long long* timing16, void* stream);
+                             int64_t kv_batch_div, float scale, long long* timing16, void* stream);
 /* Per-pixel attention over L <= 32 frames (attn_temporal.cu, register-resident mma.sync): token t of
  * sequence s lives at q + s*seq_stride + t*tok_stride (+ head*head_dim).  head_dim 64 is the fast path;
  * any head_dim <= 64, L <= 64 is served by a scalar kernel (I2VGen's 4-channel local encoder).

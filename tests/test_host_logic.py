@@ -174,6 +174,23 @@ allc = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(allc, chk)
 assert all(float(c) == float(allc[0]) for c in allc), allc
 assert nbytes == sum(p.numel() * 4 for p in m.parameters())
+# packed-arena broadcast (what the GPU path ships: fp16 GEMM matrices + fp32 vectors), here on a stand-in module whose
+# "packed" tensors live on the CPU (the real _pack() needs a CUDA device): mixed dtypes, several buckets
+class _Packed:
+    def __init__(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.t = [("a.w", torch.randn(300, 70, generator=g).half()), ("a.b", torch.randn(300, generator=g)),
+                  ("b.w", torch.randn(1000, 129, generator=g).half()), ("c.b", torch.randn(7, generator=g))]
+        self.offloaded = False
+    def packed_tensors(self):
+        return self.t
+    def offload_masters(self):
+        self.offloaded = True
+pm = _Packed(500 + rank)
+nb2 = parallel.broadcast_packed(pm, src=0, bucket_bytes=64 << 10, offload_masters=True)
+ref = _Packed(500)
+assert all(torch.equal(a[1], b[1]) for a, b in zip(pm.t, ref.t)), "every rank must hold rank 0's packed weights"
+assert nb2 == sum(t.numel() * t.element_size() for _, t in ref.t) and pm.offloaded
 prompts = [f"p{i}" for i in range(8)]
 mine = parallel.shard_items(prompts, rank, world)
 got = [None] * world

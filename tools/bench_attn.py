@@ -1,5 +1,5 @@
-"""Micro-benchmark of vgen_attention_d64 on the config-2 shapes (device time via CUDA events), for every q-tile stagger
-mode, plus the instrumented twin's per-phase cycle counters (softmax warp 0 of each q-tile of one mid-grid CTA)."""
+"""Micro-benchmark of vgen_attention_d64 / vgen_attention_d512 on the config-2 shapes (device time via CUDA events), plus
+the instrumented twin's per-phase cycle counters (softmax warp 0 of each q-tile of one mid-grid CTA)."""
 import ctypes
 import json
 import os
@@ -10,14 +10,17 @@ import torch  # noqa: E402
 from vgen_b200 import lib  # noqa: E402
 
 
-def call(q, k, v, out, h, div, stagger, timing=None):
+def call(q, k, v, out, h, div, timing=None):
     L = lib.load()
     b, lq, inner = q.shape
-    rc = L.vgen_attention_d64_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, h, lq, k.shape[1], q.stride(1),
-                                    k.stride(1), v.stride(1), out.stride(1), div, 64 ** -0.5, stagger,
-                                    timing.data_ptr() if timing is not None else None,
-                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    lib.check(rc, "vgen_attention_d64_debug")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if timing is None:
+        rc = L.vgen_attention_d64(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, h, lq, k.shape[1], q.stride(1),
+                                  k.stride(1), v.stride(1), out.stride(1), div, 64 ** -0.5, st)
+    else:
+        rc = L.vgen_attention_d64_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, h, lq, k.shape[1], q.stride(1),
+                                        k.stride(1), v.stride(1), out.stride(1), div, 64 ** -0.5, timing.data_ptr(), st)
+    lib.check(rc, "vgen_attention_d64")
 
 
 def main():
@@ -33,10 +36,9 @@ def main():
             q = torch.randn(b, lq, inner, generator=g).half().cuda()
             kv = torch.randn(b // div, lk, 2 * inner, generator=g).half().cuda()
             k, v = kv[:, :, :inner], kv[:, :, inner:]
-        outs = {}
-        for stagger in (0, 3):
+        for _once in (0,):
             out = torch.empty(b, lq, inner, device="cuda", dtype=torch.float16)
-            fn = lambda: call(q, k, v, out, h, div, stagger)  # noqa: E731
+            fn = lambda: call(q, k, v, out, h, div)  # noqa: E731
             fn()
             torch.cuda.synchronize()
             ts = []
@@ -51,18 +53,35 @@ def main():
             ms = ts[len(ts) // 2]
             flops = 4.0 * b * h * lq * lk * 64
             timing = torch.zeros(16, dtype=torch.int64, device="cuda")
-            call(q, k, v, out, h, div, stagger, timing)
+            call(q, k, v, out, h, div, timing)
             torch.cuda.synchronize()
             t = timing.cpu().tolist()
-            outs[stagger] = out.clone()
-            row = {"shape": (b, h, lq, lk, div), "stagger": stagger, "ms": round(ms, 4), "min_ms": round(ts[0], 4),
+            row = {"shape": (b, h, lq, lk, div), "ms": round(ms, 4), "min_ms": round(ts[0], 4),
                    "tflops": round(flops / ms / 1e9, 1),
                    "phase_cycles_per_block": {f"tile{i}": {n: round(t[i * 8 + j] / max(t[i * 8 + 5], 1), 1)
                                                           for j, n in enumerate(["wait_S", "ld_max", "wait_Pbuf", "exp_store", "total"])}
                                               for i in (0, 1)}}
             print(json.dumps(row), flush=True)
             res.append(row)
-        assert torch.equal(outs[0], outs[3]), "stagger must not change results"
+    from vgen_b200 import ops
+    for (b, l) in [(2, 14080), (4, 14400), (2, 1792)]:
+        qkv = torch.randn(b, l, 1536, generator=g).half().cuda()
+        q, k, v = qkv[:, :, :512], qkv[:, :, 512:1024], qkv[:, :, 1024:]
+        out = torch.empty(b, l, 512, device="cuda", dtype=torch.float16)
+        ops.attention_d512(q, k, v, out=out)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            ops.attention_d512(q, k, v, out=out)
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ts.sort()
+        row = {"d512_shape": (b, l), "ms": round(ts[2], 4), "tflops": round(4.0 * b * l * l * 512 / ts[2] / 1e9, 1)}
+        print(json.dumps(row), flush=True)
+        res.append(row)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_attn.json", "w"), indent=0)
 

@@ -248,6 +248,34 @@ def group_attention():
             report(f"attention_d64 b{b} h{heads} lq{lq} lk{lk} div{div} fused{int(fused)}", rel_err(out, sdpa(q, kk, vv, heads)), 3e-3)
         run_case(f"attn {b} {heads} {lq} {lk}", f)
 
+    # head_dim 512 single-head flash attention (VAE AttnBlock): ragged lengths, fused qkv views, the 1280x704 size,
+    # large-magnitude inputs (scores ~ +-60: fp32 statistics must hold where fp16 logits would not), batches of 3 videos
+    # through the batched temporal entry
+    for (b, lq, lk, fused, scale) in [(1, 128, 64, False, 1.0), (2, 200, 200, True, 1.0), (1, 96, 96, True, 1.0), (2, 130, 77, False, 1.0),
+                                      (3, 1792, 1792, True, 1.0), (2, 14080, 14080, True, 1.0), (1, 640, 640, True, 4.0)]:
+        def f():
+            if fused:
+                qkv = rnd(b, lq, 3 * 512, scale=scale).half()
+                q, k, v = qkv[:, :, :512], qkv[:, :, 512:1024], qkv[:, :, 1024:]
+            else:
+                q = rnd(b, lq, 512, scale=scale).half()
+                kv = rnd(b, lk, 1024, scale=scale).half()
+                k, v = kv[:, :, :512], kv[:, :, 512:]
+            out = ops.attention_d512(q, k, v)
+            torch.cuda.synchronize()
+            report(f"attention_d512 b{b} lq{lq} lk{lk} fused{int(fused)} x{scale}", rel_err(out, sdpa(q, k, v, 1)), 3e-3)
+        run_case(f"attn512 {b} {lq} {lk}", f)
+
+    def f():
+        qkv = rnd(3, 8, 200, 3 * 128).half()
+        q, k, v = qkv[..., :128], qkv[..., 128:256], qkv[..., 256:]
+        out = ops.attention_temporal(q, k, v, 2, 64)
+        torch.cuda.synchronize()
+        tq = lambda t: t.permute(0, 2, 1, 3).reshape(3 * 200, 8, 128)  # noqa: E731  [(b npix), f, inner]
+        ref = sdpa(tq(q), tq(k), tq(v), 2).reshape(3, 200, 8, 128).permute(0, 2, 1, 3)
+        report("attention_temporal batched b3 f8 npix200 h2", rel_err(out, ref), 3e-3)
+    run_case("tattn batched", f)
+
     for (f_, npix, heads, d) in [(16, 100, 1, 64), (16, 1000, 5, 64), (8, 333, 2, 64), (4, 96, 2, 64), (3, 60, 1, 64),
                                  (32, 500, 5, 64), (20, 64, 2, 64), (16, 14080, 8, 64), (16, 300, 2, 4), (4, 50, 2, 4)]:
         def f():

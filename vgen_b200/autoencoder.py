@@ -60,6 +60,10 @@ class AutoencoderKL(SpecModule):
             w = sd[p + "weight"]
             W[p + "w"], W[p + "b"] = _f16(w.reshape(w.shape[0], -1), dev), _f32(sd[p + "bias"], dev)
 
+        def fuse_qkv(a):   # one [3c, c] projection for the flash-attention path
+            W[a + "qkv.w"] = torch.cat([W[a + "q.w"], W[a + "k.w"], W[a + "v.w"]], 0).contiguous()
+            W[a + "qkv.b"] = torch.cat([W[a + "q.b"], W[a + "k.b"], W[a + "v.b"]], 0).contiguous()
+
         def resnet(p):
             norm(p + "norm1."), conv3(p + "conv1."), norm(p + "norm2."), conv3(p + "conv2.")
             if (p + "nin_shortcut.weight") in sd:
@@ -72,6 +76,7 @@ class AutoencoderKL(SpecModule):
         norm(a + "norm.")
         for nm in ("q.", "k.", "v.", "proj_out."):
             conv1(a + nm)
+        fuse_qkv(a)
         for lvl in range(len(self.plan.ch_mult)):
             for j in range(self.plan.num_res_blocks + 1):
                 resnet(f"decoder.up.{lvl}.block.{j}.")
@@ -91,6 +96,7 @@ class AutoencoderKL(SpecModule):
         norm(a + "norm.")
         for nm in ("q.", "k.", "v.", "proj_out."):
             conv1(a + nm)
+        fuse_qkv(a)
         norm("encoder.norm_out."), conv3("encoder.conv_out."), conv1("quant_conv.")
         self._packed = W
         return W
@@ -119,19 +125,26 @@ class AutoencoderKL(SpecModule):
 
     def _attn(self, x, W, p):
         """AttnBlock.forward, autoencoder.py:365-389: single-head attention over h*w tokens of width c.
-        Done as three GEMMs + a row softmax per image: S = q k^T / sqrt(c), P = softmax(S), O = P v.
-        v's bias is added after P v (rows of P sum to 1), so v^T can be produced directly as W_v g^T."""
+        c = 512 (the SD VAE) / c = 64: tcgen05 flash attention on a fused q|k|v projection -- the [hw, hw] score matrix
+        (793 MB fp32 per 1280x704 frame in the reference) never leaves the SM, scores / softmax statistics are fp32.
+        Other widths: three GEMMs + a row softmax per image (S materialised in fp16)."""
         n, h, w, c = x.shape
         hw = h * w
         g = ops.group_norm(x, W[p + "norm.g"], W[p + "norm.b"], 1e-6, False).view(n, hw, c)
-        q = ops.linear(g, W[p + "q.w"], bias=W[p + "q.b"])
-        k = ops.linear(g, W[p + "k.w"], bias=W[p + "k.b"])
-        o = torch.empty(n, hw, c, device=x.device, dtype=torch.float16)
-        for i in range(n):
-            vt = ops.linear(W[p + "v.w"], g[i])                                # [c, hw] = W_v g^T
-            s = ops.linear(q[i], k[i], alpha=float(c) ** -0.5)                 # [hw, hw]
-            ops.softmax_rows_(s, 1.0)
-            ops.linear(s, vt, bias=W[p + "v.b"], out=o[i])                     # [hw, c]
+        if c in (64, 512):
+            qkv = ops.linear(g, W[p + "qkv.w"], bias=W[p + "qkv.b"])                # [n, hw, 3c]
+            q, k, v = qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:]
+            o = ops.attention_d512(q, k, v) if c == 512 else ops.attention_d64(q, k, v, 1)
+        else:
+            q = ops.linear(g, W[p + "q.w"], bias=W[p + "q.b"])
+            k = ops.linear(g, W[p + "k.w"], bias=W[p + "k.b"])
+            o = torch.empty(n, hw, c, device=x.device, dtype=torch.float16)
+            for i in range(n):
+                # v's bias is added after P v (rows of P sum to 1), so v^T can be produced directly as W_v g^T
+                vt = ops.linear(W[p + "v.w"], g[i])                                # [c, hw] = W_v g^T
+                s = ops.linear(q[i], k[i], alpha=float(c) ** -0.5)                 # [hw, hw]
+                ops.softmax_rows_(s, 1.0)
+                ops.linear(s, vt, bias=W[p + "v.b"], out=o[i])                     # [hw, c]
         out = ops.linear(o.view(-1, c), W[p + "proj_out.w"], bias=W[p + "proj_out.b"], residual=x.view(-1, c))
         return out.view(n, h, w, c)
 

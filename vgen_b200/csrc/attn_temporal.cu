@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __half* __rest
                                                             long seq_stride_q, long tok_stride_o, long seq_stride_o,
                                                             float scale_log2, long spb, long batch_stride_q,
                                                             long batch_stride_o) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   constexpr int kRow = 72;  // halfs per smem row
   constexpr int MT = LP / 16;
   extern __shared__ __align__(16) __half sm_t[];
@@ -190,6 +191,7 @@ __global__ void attn_small_kernel(const __half* __restrict__ q, const __half* __
                                   __half* __restrict__ out, long nseq, int heads, int L, int d, long tok_stride,
                                   long seq_stride, long tok_stride_o, long seq_stride_o, float scale, long spb,
                                   long batch_stride, long batch_stride_o) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nseq * heads * L) return;
   const int i = (int)(idx % L);
@@ -247,7 +249,7 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
     const float sl2 = scale * 1.4426950408889634f;
     if (L <= 16) {
       const size_t smem = 4 * 3 * 16 * 72 * sizeof(__half);
-      attn_temporal_kernel<16><<<blocks, 128, smem, st>>>(qp, kp, vp, op, nseq, (int)heads, (int)L, tok_stride, seq_stride,
+      launch_kernel(attn_temporal_kernel<16>, dim3(blocks), dim3(128), smem, st, qp, kp, vp, op, nseq, (int)heads, (int)L, tok_stride, seq_stride,
                                                           tok_stride_o, seq_stride_o, sl2, spb, batch_stride, batch_stride_o);
     } else {
       const size_t smem = 4 * 3 * 32 * 72 * sizeof(__half);
@@ -256,7 +258,7 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
         VG_CUDA(cudaFuncSetAttribute(attn_temporal_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_once.mark();
       }
-      attn_temporal_kernel<32><<<blocks, 128, smem, st>>>(qp, kp, vp, op, nseq, (int)heads, (int)L, tok_stride, seq_stride,
+      launch_kernel(attn_temporal_kernel<32>, dim3(blocks), dim3(128), smem, st, qp, kp, vp, op, nseq, (int)heads, (int)L, tok_stride, seq_stride,
                                                           tok_stride_o, seq_stride_o, sl2, spb, batch_stride, batch_stride_o);
     }
     VG_LAUNCH_CHECK("attn_temporal_kernel");
@@ -264,7 +266,7 @@ extern "C" int vgen_attention_temporal(const void* q, const void* k, const void*
   }
   VG_REQUIRE(head_dim <= 64 && L <= 64, "vgen_attention_temporal: unsupported (head_dim, L)");
   const long total = nseq * heads * L;
-  attn_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(qp, kp, vp, op, nseq, (int)heads, (int)L, (int)head_dim,
+  launch_kernel(attn_small_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, qp, kp, vp, op, nseq, (int)heads, (int)L, (int)head_dim,
                                                                     tok_stride, seq_stride, tok_stride_o, seq_stride_o, scale, spb,
                                                                     batch_stride, batch_stride_o);
   VG_LAUNCH_CHECK("attn_small_kernel");

@@ -1,6 +1,8 @@
 // Library-wide host state: last error, launch counter, device properties, tensor-map encoding.
 #include "common.h"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -22,6 +24,15 @@ int check_cuda(cudaError_t e, const char* what) {
   return 2;
 }
 const std::string& last_error() { return g_last_error; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VGEN_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int current_device() {
   int dev = 0;

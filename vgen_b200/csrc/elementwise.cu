@@ -15,6 +15,7 @@ __device__ __forceinline__ float silu_e(float v) { return __fdividef(v, 1.0f + _
 // the result leaves as fp16 [b, c, f, h, w] (:276).  Inside, everything is channels-last.
 template <typename Tin>
 __global__ void cp_to_pc_kernel(const Tin* __restrict__ x, __half* __restrict__ y, long n, int c, long p, int c_pad) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * p * c_pad) return;
   const int ci = (int)(idx % c_pad);
@@ -26,6 +27,7 @@ __global__ void cp_to_pc_kernel(const Tin* __restrict__ x, __half* __restrict__ 
 }
 template <typename Tout>
 __global__ void pc_to_cp_kernel(const __half* __restrict__ x, Tout* __restrict__ y, long n, int c, long p, long ldx) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * p * c) return;
   const long pi = idx % p;
@@ -47,6 +49,7 @@ __global__ void pc_to_cp_kernel<__half>(const __half* __restrict__ x, __half* __
 // out[(n,oy,ox)][(ky*kw+kx)*c + ci] = act(x[n][oy*s-pt+ky][ox*s-pl+kx][ci]); columns >= kh*kw*c are zero.
 __global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__ out, long nimg, int h, int w, int c,
                               int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int kpad, int act_silu) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const bool vec = (c % 8 == 0);
   const int kv = vec ? kpad / 8 : kpad;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,6 +97,7 @@ __global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__
 
 // ------------------------------------------------------------------ nearest x2 upsample (channels-last)
 __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nimg, int h, int w, int c8) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = nimg * (2L * h) * (2L * w) * c8;
   if (idx >= total) return;
@@ -109,6 +113,7 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 // ------------------------------------------------------------------ 2-D strided copy (channel concat)
 __global__ void copy2d_kernel(const __half* __restrict__ src, long lds, __half* __restrict__ dst, long ldd, long rows,
                               int cols) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const bool vec = (cols % 8 == 0) && (lds % 8 == 0) && (ldd % 8 == 0) &&
                    (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,6 +135,7 @@ __global__ void copy2d_kernel(const __half* __restrict__ src, long lds, __half* 
 // op: 0 silu(a)  1 a+b  2 gelu(a) (erf)  3 a*s  4 a + s*b
 __global__ void eltwise_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ y, long n,
                                int op, float s) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const float x = __half2float(a[idx]);
@@ -149,6 +155,7 @@ __global__ void eltwise_kernel(const __half* __restrict__ a, const __half* __res
 __global__ void linear_small_kernel(const __half* __restrict__ a, long lda, const __half* __restrict__ w,
                                     const float* __restrict__ bias, const __half* __restrict__ res, long ldr,
                                     __half* __restrict__ out, long ldo, long m, int n, int k, int silu_in, int gelu_out) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long warp_id = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_id >= m * n) return;
@@ -177,6 +184,7 @@ __global__ void linear_small_kernel(const __half* __restrict__ a, long lda, cons
 __global__ void linear_tinyk_kernel(const __half* __restrict__ a, long lda, const __half* __restrict__ w,
                                     const float* __restrict__ bias, const __half* __restrict__ res, long ldr,
                                     __half* __restrict__ out, long ldo, long m, int n, int k, int silu_in, int gelu_out) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m * n) return;
   const long mi = idx / n;
@@ -199,6 +207,7 @@ __global__ void linear_tinyk_kernel(const __half* __restrict__ a, long lda, cons
 // ------------------------------------------------------------------ sinusoidal embedding
 // tools/modules/unet/util.py:178-190: outer(t, 10000^(-i/half)), cat[cos, sin]; fp32 math, fp16 store
 __global__ void sinusoidal_kernel(const float* __restrict__ t, __half* __restrict__ out, int b, int dim) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (idx >= b * half) return;
@@ -211,6 +220,7 @@ __global__ void sinusoidal_kernel(const float* __restrict__ t, __half* __restric
 
 // ------------------------------------------------------------------ row softmax (in place, fp16 rows)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long ld, int n, float scale) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   __shared__ float red[8];
   __half* row = x + (long)blockIdx.x * ld;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -238,6 +248,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 // ------------------------------------------------------------------ adaptive average pool (channels-last)
 __global__ void adaptive_avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nimg, int h, int w, int c,
                                         int oh, int ow, int silu_in) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nimg * oh * ow * c) return;
   const int ci = (int)(idx % c);
@@ -268,6 +279,7 @@ struct DdimCoef {
 __global__ void ddim_step_kernel(float* __restrict__ xt, const __half* __restrict__ y, const __half* __restrict__ u,
                                  const float* __restrict__ noise, long n, float guide, int has_u, DdimCoef k, int mean_v,
                                  float* __restrict__ x0_out) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float out;
@@ -298,6 +310,7 @@ __global__ void ddim_step_kernel(float* __restrict__ xt, const __half* __restric
 // fp32 in the reference layout [n][zc][p].
 __global__ void vae_sample_kernel(const __half* __restrict__ mom, const float* __restrict__ noise, float* __restrict__ z,
                                   long n, int zc, long p, float scale) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * zc * p) return;
   const long pi = idx % p;
@@ -324,9 +337,9 @@ int vgen_cp_to_pc(const void* x, int x_is_f32, void* y, int64_t n, int64_t c, in
   if (total == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (x_is_f32)
-    cp_to_pc_kernel<float><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<__half*>(y), n, (int)c, p, (int)c_pad);
+    launch_kernel(cp_to_pc_kernel<float>, dim3(nblk(total, 256)), dim3(256), 0, st, reinterpret_cast<const float*>(x), reinterpret_cast<__half*>(y), n, (int)c, p, (int)c_pad);
   else
-    cp_to_pc_kernel<__half><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n, (int)c, p, (int)c_pad);
+    launch_kernel(cp_to_pc_kernel<__half>, dim3(nblk(total, 256)), dim3(256), 0, st, reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n, (int)c, p, (int)c_pad);
   VG_LAUNCH_CHECK("cp_to_pc_kernel");
   return 0;
 }
@@ -337,9 +350,9 @@ int vgen_pc_to_cp(const void* x, int64_t ldx, void* y, int y_is_f32, int64_t n, 
   if (total == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (y_is_f32)
-    pc_to_cp_kernel<float><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<float*>(y), n, (int)c, p, ldx);
+    launch_kernel(pc_to_cp_kernel<float>, dim3(nblk(total, 256)), dim3(256), 0, st, reinterpret_cast<const __half*>(x), reinterpret_cast<float*>(y), n, (int)c, p, ldx);
   else
-    pc_to_cp_kernel<__half><<<nblk(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n, (int)c, p, ldx);
+    launch_kernel(pc_to_cp_kernel<__half>, dim3(nblk(total, 256)), dim3(256), 0, st, reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n, (int)c, p, ldx);
   VG_LAUNCH_CHECK("pc_to_cp_kernel");
   return 0;
 }
@@ -353,7 +366,7 @@ int vgen_im2col(const void* x, void* out, int64_t nimg, int64_t h, int64_t w, in
   const long rows = nimg * ho * wo;
   const long total = rows * (c % 8 == 0 ? kpad / 8 : kpad);
   if (total == 0) return 0;
-  im2col_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(im2col_kernel, dim3(nblk(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), nimg, (int)h, (int)w, (int)c, (int)kh, (int)kw,
       (int)stride, (int)pad_t, (int)pad_l, (int)ho, (int)wo, (int)kpad, act_silu);
   VG_LAUNCH_CHECK("im2col_kernel");
@@ -364,7 +377,7 @@ int vgen_upsample_nearest2x(const void* x, void* y, int64_t nimg, int64_t h, int
   VG_REQUIRE(x && y && c % 8 == 0, "vgen_upsample_nearest2x: C must be a multiple of 8");
   const long total = nimg * 4 * h * w * (c / 8);
   if (total == 0) return 0;
-  upsample2x_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(upsample2x_kernel, dim3(nblk(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), nimg, (int)h, (int)w, (int)(c / 8));
   VG_LAUNCH_CHECK("upsample2x_kernel");
   return 0;
@@ -376,7 +389,7 @@ int vgen_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t ro
   const bool vec = (cols % 8 == 0) && (lds % 8 == 0) && (ldd % 8 == 0) &&
                    (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
   const long total = vec ? rows * (cols / 8) : rows * cols;
-  copy2d_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(copy2d_kernel, dim3(nblk(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst), ldd, rows, (int)cols);
   VG_LAUNCH_CHECK("copy2d_kernel");
   return 0;
@@ -386,7 +399,7 @@ int vgen_eltwise(int op, const void* a, const void* b, void* y, int64_t n, float
   VG_REQUIRE(a && y && op >= 0 && op <= 4, "vgen_eltwise: bad arguments");
   VG_REQUIRE(!(op == 1 || op == 4) || b, "vgen_eltwise: binary op needs b");
   if (n == 0) return 0;
-  eltwise_kernel<<<nblk(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(eltwise_kernel, dim3(nblk(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(a), reinterpret_cast<const __half*>(b), reinterpret_cast<__half*>(y), n, op, s);
   VG_LAUNCH_CHECK("eltwise_kernel");
   return 0;
@@ -398,12 +411,12 @@ int vgen_linear_small(const void* a, int64_t m, int64_t k, int64_t lda, const vo
   if (m == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (k <= 32) {
-    linear_tinyk_kernel<<<nblk(m * n, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(w),
+    launch_kernel(linear_tinyk_kernel, dim3(nblk(m * n, 256)), dim3(256), 0, st, reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(w),
                                                          bias, reinterpret_cast<const __half*>(res), ldr,
                                                          reinterpret_cast<__half*>(out), ldo, m, (int)n, (int)k, silu_in, gelu_out);
     VG_LAUNCH_CHECK("linear_tinyk_kernel");
   } else {
-    linear_small_kernel<<<nblk(m * n * 32, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(w),
+    launch_kernel(linear_small_kernel, dim3(nblk(m * n * 32, 256)), dim3(256), 0, st, reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(w),
                                                               bias, reinterpret_cast<const __half*>(res), ldr,
                                                               reinterpret_cast<__half*>(out), ldo, m, (int)n, (int)k, silu_in, gelu_out);
     VG_LAUNCH_CHECK("linear_small_kernel");
@@ -413,7 +426,7 @@ int vgen_linear_small(const void* a, int64_t m, int64_t k, int64_t lda, const vo
 
 int vgen_sinusoidal_embedding(const float* t, void* out, int64_t b, int64_t dim, void* stream) {
   VG_REQUIRE(t && out && b > 0 && dim > 0 && dim % 2 == 0, "vgen_sinusoidal_embedding: bad arguments");
-  sinusoidal_kernel<<<nblk(b * dim / 2, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, reinterpret_cast<__half*>(out), (int)b, (int)dim);
+  launch_kernel(sinusoidal_kernel, dim3(nblk(b * dim / 2, 128)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), t, reinterpret_cast<__half*>(out), (int)b, (int)dim);
   VG_LAUNCH_CHECK("sinusoidal_kernel");
   return 0;
 }
@@ -421,7 +434,7 @@ int vgen_sinusoidal_embedding(const float* t, void* out, int64_t b, int64_t dim,
 int vgen_softmax_rows(void* x, int64_t rows, int64_t n, int64_t ld, float scale, void* stream) {
   VG_REQUIRE(x && rows >= 0 && n > 0 && ld >= n, "vgen_softmax_rows: bad arguments");
   if (rows == 0) return 0;
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<__half*>(x), ld, (int)n, scale);
+  launch_kernel(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__half*>(x), ld, (int)n, scale);
   VG_LAUNCH_CHECK("softmax_rows_kernel");
   return 0;
 }
@@ -431,7 +444,7 @@ int vgen_adaptive_avgpool(const void* x, void* y, int64_t nimg, int64_t h, int64
   VG_REQUIRE(x && y && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "vgen_adaptive_avgpool: bad arguments");
   const long total = nimg * oh * ow * c;
   if (total == 0) return 0;
-  adaptive_avgpool_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(adaptive_avgpool_kernel, dim3(nblk(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), nimg, (int)h, (int)w, (int)c, (int)oh, (int)ow, silu_in);
   VG_LAUNCH_CHECK("adaptive_avgpool_kernel");
   return 0;
@@ -442,7 +455,7 @@ int vgen_vae_sample(const void* moments, const float* noise, float* z, int64_t n
   VG_REQUIRE(moments && noise && z && n >= 0 && zc > 0 && p > 0, "vgen_vae_sample: bad arguments");
   const long total = n * zc * p;
   if (total == 0) return 0;
-  vae_sample_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(vae_sample_kernel, dim3(nblk(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(moments), noise, z, n, (int)zc, p, scale);
   VG_LAUNCH_CHECK("vae_sample_kernel");
   return 0;
@@ -455,7 +468,7 @@ int vgen_ddim_step(float* xt, const void* y, const void* u, const float* noise, 
   DdimCoef k;
   for (int i = 0; i < 7; ++i) k.c[i] = coef7[i];
   k.c[7] = 0.f;
-  ddim_step_kernel<<<nblk(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(ddim_step_kernel, dim3(nblk(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       xt, reinterpret_cast<const __half*>(y), reinterpret_cast<const __half*>(u), noise, n, guide_scale, u != nullptr, k,
       mean_type_v, x0_out);
   VG_LAUNCH_CHECK("ddim_step_kernel");

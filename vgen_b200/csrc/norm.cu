@@ -53,6 +53,7 @@ __device__ __forceinline__ void acc8(const uint4& u, float (&s)[8], float (&q)[8
 
 template <int VPT>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, float2* __restrict__ partial, GnGeom g) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   extern __shared__ float sm[];  // [2][rows][C]
   const int n = blockIdx.y, sp = blockIdx.x;
   const int tid = threadIdx.x;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
 // one warp per group: lanes stride over the splits, then a shuffle tree of Chan merges
 __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats,
                                                            GnGeom g, float eps) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int n = blockIdx.x;
   const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float cnt = 0.f, mean = 0.f, m2 = 0.f;
@@ -172,19 +174,6 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float2* __restr
 // x * sigmoid(x); the quotient uses the approximate reciprocal (<= 1 ulp, the result is rounded to fp16): the
 // IEEE division sequence (~10 instructions) made gn_apply issue-bound (ncu r01k: 65% issue, 67% XU at 3.5 TB/s)
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
-// Variant with the reciprocal on the FMA pipe: gn_apply sits at 67 % of the XU (MUFU) pipe with two MUFU per element
-// (ex2 + rcp) while the FMA pipe is at 33 %.  1 / d for d = 1 + 2^t in [1, 2^126]: exponent-negation estimate (10 %),
-// three Newton steps (1.5e-7) = 6 FMA-pipe + 1 ALU instructions instead of one MUFU.
-__device__ __forceinline__ float silu_fma(float v) {
-  const float t = fminf(v * -1.4426950408889634f, 126.0f);
-  const float d = 1.0f + fast_exp2(t);
-  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
-  r = r * fmaf(-d, r, 2.0f);
-  r = r * fmaf(-d, r, 2.0f);
-  r = r * fmaf(-d, r, 2.0f);
-  return v * r;
-}
-
 __device__ __forceinline__ uint4 norm8(const uint4& u, const float (&sc)[8], const float (&sh)[8], int silu) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&u);
   float f[8];
@@ -194,10 +183,7 @@ __device__ __forceinline__ uint4 norm8(const uint4& u, const float (&sc)[8], con
     f[2 * k] = fmaf(t.x, sc[2 * k], sh[2 * k]);
     f[2 * k + 1] = fmaf(t.y, sc[2 * k + 1], sh[2 * k + 1]);
   }
-  if (silu == 2) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = silu_fma(f[k]);
-  } else if (silu) {
+  if (silu) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
   }
@@ -213,6 +199,7 @@ template <int VPT>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                        const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, GnGeom g, int silu, long apply_chunk) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
   const int r = tid / g.cols, cv = tid - r * g.cols;
@@ -283,6 +270,7 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long rows, int C, long ldx, long ldy, float eps) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int lane = threadIdx.x & 31;
   const int C8 = C >> 3;
   const long warps_total = (long)gridDim.x * (blockDim.x >> 5);
@@ -375,6 +363,7 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 long rows, int C, long ldx, long ldy, float eps) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   constexpr int RW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, li = lane % LPR;
@@ -462,6 +451,7 @@ __global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __
 __global__ void layernorm_small_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, long rows, int C,
                                        long ldx, long ldy, float eps) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const __half* xr = x + row * ldx;
@@ -499,12 +489,6 @@ int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, con
   GnGeom g;
   int rc = gn_geometry(n, p, (int)c, &g);
   if (rc) return rc;
-  static int silu_mode = -1;   // VGEN_GN_SILU: 1 = MUFU reciprocal, 2 = FMA-pipe reciprocal (tuning knob, read once)
-  if (silu_mode < 0) {
-    const char* e = getenv("VGEN_GN_SILU");
-    silu_mode = e ? atoi(e) : 1;
-  }
-  if (silu) silu = silu_mode == 2 ? 2 : 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float2* part = reinterpret_cast<float2*>(workspace);
   float2* stats = part + (long)n * kMaxSplits * kGroups;
@@ -513,11 +497,11 @@ int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, con
   dim3 grid_s(g.splits, (unsigned)n);
   const int threads = g.rows * g.cols < 32 ? 32 : g.rows * g.cols;
   if (g.vpt == 1)
-    gn_stats_kernel<1><<<grid_s, threads, smem_stats, st>>>(reinterpret_cast<const __half*>(x), part, g);
+    launch_kernel(gn_stats_kernel<1>, dim3(grid_s), dim3(threads), smem_stats, st, reinterpret_cast<const __half*>(x), part, g);
   else
-    gn_stats_kernel<2><<<grid_s, threads, smem_stats, st>>>(reinterpret_cast<const __half*>(x), part, g);
+    launch_kernel(gn_stats_kernel<2>, dim3(grid_s), dim3(threads), smem_stats, st, reinterpret_cast<const __half*>(x), part, g);
   VG_LAUNCH_CHECK("gn_stats_kernel");
-  gn_finalize_kernel<<<(unsigned)n, 1024, 0, st>>>(part, stats, g, eps);
+  launch_kernel(gn_finalize_kernel, dim3((unsigned)n), dim3(1024), 0, st, part, stats, g, eps);
   VG_LAUNCH_CHECK("gn_finalize_kernel");
   long blocks = (8L * sm_count()) / n;
   if (blocks < 1) blocks = 1;
@@ -526,10 +510,10 @@ int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, con
   blocks = (p + apply_chunk - 1) / apply_chunk;
   dim3 grid_a((unsigned)blocks, (unsigned)n);
   if (g.vpt == 1)
-    gn_apply_kernel<1><<<grid_a, threads, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), stats, gamma,
+    launch_kernel(gn_apply_kernel<1>, dim3(grid_a), dim3(threads), 0, st, reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), stats, gamma,
                                                    beta, g, silu, apply_chunk);
   else
-    gn_apply_kernel<2><<<grid_a, threads, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), stats, gamma,
+    launch_kernel(gn_apply_kernel<2>, dim3(grid_a), dim3(threads), 0, st, reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), stats, gamma,
                                                    beta, g, silu, apply_chunk);
   VG_LAUNCH_CHECK("gn_apply_kernel");
   return 0;
@@ -557,24 +541,24 @@ int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx
       long gblocks = ((rows + rw - 1) / rw + wpb - 1) / wpb;
       if (gblocks > cap) gblocks = cap;
       if (c8 == 40)
-        layernorm_grouped_kernel<8, 5><<<(unsigned)gblocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+        launch_kernel(layernorm_grouped_kernel<8, 5>, dim3((unsigned)gblocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
       else
-        layernorm_grouped_kernel<16, 5><<<(unsigned)gblocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+        launch_kernel(layernorm_grouped_kernel<16, 5>, dim3((unsigned)gblocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
       VG_LAUNCH_CHECK("layernorm_grouped_kernel");
       return 0;
     }
     if (c8 <= 32)
-      layernorm_kernel<1><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      launch_kernel(layernorm_kernel<1>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     else if (c8 <= 64)
-      layernorm_kernel<2><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      launch_kernel(layernorm_kernel<2>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     else if (c8 <= 160)
-      layernorm_kernel<5><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      launch_kernel(layernorm_kernel<5>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     else
-      layernorm_kernel<10><<<(unsigned)blocks, 32 * wpb, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+      launch_kernel(layernorm_kernel<10>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     VG_LAUNCH_CHECK("layernorm_kernel");
   } else {
     const unsigned blocks = (unsigned)((rows + 127) / 128);
-    layernorm_small_kernel<<<blocks, 128, 0, st>>>(xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
+    launch_kernel(layernorm_small_kernel, dim3(blocks), dim3(128), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
     VG_LAUNCH_CHECK("layernorm_small_kernel");
   }
   return 0;

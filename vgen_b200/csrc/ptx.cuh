@@ -86,6 +86,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// pdl_launch_dependents(): the next kernel in the stream may be scheduled once every CTA of this grid has got here
+// (or exited); pdl_wait(): block until every prerequisite grid has completed and its writes are visible.  Rule for
+// every kernel of the library: no global-memory access before pdl_wait().  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {   // simple kernels: both at the very top
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 // ----------------------------------------------------------------------------- fences
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -14,6 +14,7 @@ namespace vg {
 
 __global__ void cfg_combine_kernel(const __half* __restrict__ y, const __half* __restrict__ u, __half* __restrict__ out,
                                    long n_per, float g, double* __restrict__ stats) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long b = blockIdx.y;
   const __half* yb = y + b * n_per;
   const __half* ub = u + b * n_per;
@@ -54,6 +55,7 @@ __global__ void cfg_combine_kernel(const __half* __restrict__ y, const __half* _
 __global__ void gauss_x0_kernel(const float* __restrict__ xt, const __half* __restrict__ out, const double* __restrict__ stats,
                                 float guide_rescale, float alpha, float sigma, int pred, float* __restrict__ x0, long n_per,
                                 long total) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   float o = __half2float(out[idx]);
@@ -81,6 +83,7 @@ __global__ void gauss_x0_kernel(const float* __restrict__ xt, const __half* __re
 __global__ void lincomb_f32_kernel(float* __restrict__ out, long n, const float* __restrict__ x0, float a0,
                                    const float* __restrict__ x1, float a1, const float* __restrict__ x2, float a2,
                                    const float* __restrict__ x3, float a3) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float r = a0 * x0[idx];
@@ -106,7 +109,7 @@ int vgen_cfg_combine(const void* y, const void* u, void* out, int64_t batch, int
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, (unsigned)batch);
-  cfg_combine_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(y), reinterpret_cast<const __half*>(u),
+  launch_kernel(cfg_combine_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __half*>(y), reinterpret_cast<const __half*>(u),
                                            reinterpret_cast<__half*>(out), n_per, guide_scale, stats);
   VG_LAUNCH_CHECK("cfg_combine_kernel");
   return 0;
@@ -116,7 +119,7 @@ int vgen_gauss_x0(const float* xt, const void* out, const double* stats, float g
                   int pred_type, float* x0, int64_t batch, int64_t n_per, void* stream) {
   VG_REQUIRE(xt && out && x0 && batch > 0 && n_per > 1 && pred_type >= 0 && pred_type <= 2, "vgen_gauss_x0: bad arguments");
   const long total = batch * n_per;
-  gauss_x0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(gauss_x0_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       xt, reinterpret_cast<const __half*>(out), stats, guide_rescale, alpha, sigma, pred_type, x0, n_per, total);
   VG_LAUNCH_CHECK("gauss_x0_kernel");
   return 0;
@@ -126,7 +129,7 @@ int vgen_lincomb_f32(float* out, int64_t n, const float* x0, float a0, const flo
                      const float* x3, float a3, void* stream) {
   VG_REQUIRE(out && x0 && n >= 0, "vgen_lincomb_f32: bad arguments");
   if (n == 0) return 0;
-  lincomb_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, n, x0, a0, x1, a1,
+  launch_kernel(lincomb_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), out, n, x0, a0, x1, a1,
                                                                                                    x2, a2, x3, a3);
   VG_LAUNCH_CHECK("lincomb_f32_kernel");
   return 0;

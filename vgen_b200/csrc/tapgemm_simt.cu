@@ -3,6 +3,7 @@
 // (VGEN_TAPGEMM_IMPL=simt) and to serve channel counts that are not a multiple of 64.
 // One thread per (row, n): slow, obviously-correct.
 #include "common.h"
+#include "ptx.cuh"
 #include "tapgemm.h"
 
 namespace vg {
@@ -11,6 +12,7 @@ __device__ __forceinline__ float gelu_erf_s(float x) { return 0.5f * x * (1.0f +
 
 __global__ void tapgemm_simt_kernel(const __half* __restrict__ A, long st1, long st2, long st3,
                                     const __half* __restrict__ W, TapGemmShape s, TapGemmEpilogue e) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long rows = (long)s.d1 * s.d2 * s.d3;
   const int out_n = e.geglu ? s.n / 2 : s.n;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,7 +66,7 @@ int tapgemm_simt_launch(const TapGemmArgs& a, cudaStream_t stream) {
   const int threads = 256;
   const long blocks = (total + threads - 1) / threads;
   VG_REQUIRE(blocks < (1L << 31), "tapgemm_simt: problem too large");
-  tapgemm_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(a.a, a.a_stride1, a.a_stride2, a.a_stride3, a.w, s,
+  launch_kernel(tapgemm_simt_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, a.a, a.a_stride1, a.a_stride2, a.a_stride3, a.w, s,
                                                                a.epi);
   VG_LAUNCH_CHECK("tapgemm_simt_kernel");
   return 0;

@@ -50,6 +50,7 @@ struct alignas(64) TapGemmKernelParams {
 
 template <bool kGeglu>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid_constant__ TapGemmKernelParams p) {
+  pdl_launch_dependents();   // PDL: the next kernel's CTAs may be scheduled as this grid's CTAs retire
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment is required by the 128B swizzle atom (8 rows x 128 B).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // prologue overlapped the previous kernel; its outputs are needed from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -310,8 +312,8 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
   int grid = sm_count();
   if (grid > s.total_tiles) grid = s.total_tiles;
   if (grid < 1) return 0;
-  if (a.epi.geglu) tapgemm_sm100_kernel<true><<<grid, kThreads, smem, stream>>>(p);
-  else tapgemm_sm100_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+  if (a.epi.geglu) launch_kernel(tapgemm_sm100_kernel<true>, dim3(grid), dim3(kThreads), smem, stream, p);
+  else launch_kernel(tapgemm_sm100_kernel<false>, dim3(grid), dim3(kThreads), smem, stream, p);
   VG_LAUNCH_CHECK("tapgemm_sm100_kernel");
   return 0;
 }

@@ -19,6 +19,7 @@ __global__ void attn_cross_small_kernel(const __half* __restrict__ q, const __ha
                                         const __half* __restrict__ v, __half* __restrict__ out, long batch, int heads,
                                         int lq, int lk, int d, long ldq, long ldk, long ldv, long ldo, int kv_batch_div,
                                         float scale) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= batch * heads * lq) return;
@@ -69,6 +70,7 @@ __global__ void attn_cross_small_kernel(const __half* __restrict__ q, const __ha
 // middle axis: src = (dst + 0.5) * lin/lout - 0.5 clamped at 0, neighbours clamped at lin-1.
 __global__ void interp_linear_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nseq, int lin, int lout,
                                           int c) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nseq * lout * c) return;
   const int ch = (int)(idx % c);
@@ -94,6 +96,7 @@ constexpr int kFfSlices = 4;
 __global__ void __launch_bounds__(kFfChan* kFfSlices)
     fourier_lowfreq_kernel(const __half* __restrict__ x, __half* __restrict__ y, int h, int w, int c, long ldx, long ldy,
                            float scale) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   extern __shared__ float sm[];
   float* cy = sm;            // cos(2 pi y / h)
   float* sy = cy + h;
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(kFfChan* kFfSlices)
 // the first and last row, util.py:799-801); 8 channels per thread.
 __global__ void upsample2x_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nimg, int h, int w, int cv,
                                        int row0, int rows_out) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = nimg * rows_out * (2L * w) * cv;
   if (idx >= total) return;
@@ -163,6 +167,7 @@ __global__ void upsample2x_rows_kernel(const __half* __restrict__ x, __half* __r
 
 __global__ void scale_copy2d_kernel(const __half* __restrict__ src, long lds, __half* __restrict__ dst, long ldd, long rows,
                                     int cols, float s) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   const long r = idx / cols;
@@ -187,7 +192,7 @@ int vgen_attention_cross_small(const void* q, const void* k, const void* v, void
              "vgen_attention_cross_small: bad shape");
   if (batch == 0) return 0;
   const long warps = batch * heads * lq;
-  attn_cross_small_kernel<<<nblk(warps * 32, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(attn_cross_small_kernel, dim3(nblk(warps * 32, 128)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(k), reinterpret_cast<const __half*>(v),
       reinterpret_cast<__half*>(out), batch, (int)heads, (int)lq, (int)lk, (int)head_dim, ldq, ldk, ldv, ldo,
       (int)kv_batch_div, scale);
@@ -199,7 +204,7 @@ int vgen_interp_linear_rows(const void* x, void* y, int64_t nseq, int64_t lin, i
   VG_REQUIRE(x && y && nseq >= 0 && lin > 0 && lout > 0 && c > 0, "vgen_interp_linear_rows: bad arguments");
   const long total = nseq * lout * c;
   if (total == 0) return 0;
-  interp_linear_rows_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(interp_linear_rows_kernel, dim3(nblk(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), nseq, (int)lin, (int)lout, (int)c);
   VG_LAUNCH_CHECK("interp_linear_rows_kernel");
   return 0;
@@ -214,7 +219,7 @@ int vgen_fourier_lowfreq_filter(const void* x, int64_t ldx, void* y, int64_t ldy
   const size_t smem = (2 * (h + w) + kFfSlices * 7 * kFfChan) * sizeof(float);
   VG_REQUIRE(smem <= 48 * 1024, "vgen_fourier_lowfreq_filter: plane too large");
   dim3 grid((unsigned)((c + kFfChan - 1) / kFfChan), (unsigned)nimg), block(kFfChan, kFfSlices);
-  fourier_lowfreq_kernel<<<grid, block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(fourier_lowfreq_kernel, dim3(grid), dim3(block), smem, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), (int)h, (int)w, (int)c, ldx, ldy, scale);
   VG_LAUNCH_CHECK("fourier_lowfreq_kernel");
   return 0;
@@ -226,7 +231,7 @@ int vgen_upsample_nearest2x_rows(const void* x, void* y, int64_t nimg, int64_t h
              "vgen_upsample_nearest2x_rows: bad arguments (C must be a multiple of 8, rows within 2h)");
   const long total = nimg * rows_out * 2 * w * (c / 8);
   if (total == 0) return 0;
-  upsample2x_rows_kernel<<<nblk(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(upsample2x_rows_kernel, dim3(nblk(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), nimg, (int)h, (int)w, (int)(c / 8), (int)row0,
       (int)rows_out);
   VG_LAUNCH_CHECK("upsample2x_rows_kernel");
@@ -237,7 +242,7 @@ int vgen_scale_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int6
                       void* stream) {
   VG_REQUIRE(src && dst && rows >= 0 && cols > 0 && lds >= cols && ldd >= cols, "vgen_scale_copy2d: bad arguments");
   if (rows == 0) return 0;
-  scale_copy2d_kernel<<<nblk(rows * cols, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(scale_copy2d_kernel, dim3(nblk(rows * cols, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst), ldd, rows, (int)cols, s);
   VG_LAUNCH_CHECK("scale_copy2d_kernel");
   return 0;

@@ -11,6 +11,7 @@
 // fp32 * 255, truncation toward zero (numpy float32 -> uint8 cast).
 // The kernel also counts, per frame, the bytes in [117, 137] -- the "last frame is grey" anomaly test of :199-201.
 #include "common.h"
+#include "ptx.cuh"
 
 namespace vg {
 
@@ -23,6 +24,7 @@ __device__ __forceinline__ unsigned to_u8(float x, float sd, float mn) {
 __global__ void __launch_bounds__(256) video_to_rgb8_kernel(const float* __restrict__ vid, uint8_t* __restrict__ out,
                                                             unsigned long long* __restrict__ band, int C, long F, long HW,
                                                             float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   // grid.y = frame; x over groups of 4 pixels
   const long f = blockIdx.y;
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,7 +89,7 @@ extern "C" int vgen_video_to_rgb8(const float* video, int64_t c, int64_t f, int6
   if (band_count) VG_CUDA(cudaMemsetAsync(band_count, 0, sizeof(unsigned long long) * f, st));
   const long hw = h * w;
   dim3 grid((unsigned)cdiv(cdiv(hw, 4), 256), (unsigned)f);
-  video_to_rgb8_kernel<<<grid, 256, 0, st>>>(video, out, band_count, (int)c, f, hw, mean3[0], mean3[1], mean3[2], std3[0],
+  launch_kernel(video_to_rgb8_kernel, dim3(grid), dim3(256), 0, st, video, out, band_count, (int)c, f, hw, mean3[0], mean3[1], mean3[2], std3[0],
                                              std3[1], std3[2]);
   VG_LAUNCH_CHECK("video_to_rgb8_kernel");
   return 0;

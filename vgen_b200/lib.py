@@ -51,7 +51,8 @@ _SIGNATURES = {
     "vgen_group_norm": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _f32, _i32, _vp, _vp],
     "vgen_layer_norm": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _f32, _vp],
     "vgen_attention_d64": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
-    "vgen_attention_d64_debug": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _vp, _vp],
+    "vgen_attention_d512": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
+    "vgen_attention_d64_debug": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _vp],
     "vgen_attention_temporal": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "vgen_softmax_rows": [_vp, _i64, _i64, _i64, _f32, _vp],
     "vgen_attention_cross_small": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],

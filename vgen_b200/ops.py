@@ -274,6 +274,27 @@ def attention_d64(q, k, v, heads, kv_batch_div=1, out=None):
     return out
 
 
+def attention_d512(q, k, v, out=None):
+    """Single-head flash attention, head_dim 512: q [b, lq, 512], k/v [b, lk, 512] (last-dim-contiguous views allowed,
+    e.g. slices of a fused qkv buffer) -> [b, lq, 512]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk16(t, nm)
+        if t.dim() != 3 or t.shape[2] != 512 or t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise _l.VgenError(f"attention_d512: {nm} must be [b, l, 512] with dense batch stride")
+    b, lq, _ = q.shape
+    lk = k.shape[1]
+    if k.shape[0] != b or v.shape != k.shape:
+        raise _l.VgenError("attention_d512: shape mismatch")
+    if out is None:
+        out = torch.empty(b, lq, 512, device=q.device, dtype=torch.float16)
+    rc = _run("attention_d512", 4.0 * b * lq * lk * 512, 2.0 * (2 * b * lq * 512 + 2 * b * lk * 512),
+              lambda: _l.load().vgen_attention_d512(_p(q), _p(k), _p(v), _p(out), b, lq, lk, q.stride(1), k.stride(1), v.stride(1),
+                                                    out.stride(1), 512 ** -0.5, _stream()),
+              tag=f"b{b} lq{lq} lk{lk}")
+    _l.check(rc, "vgen_attention_d512")
+    return out
+
+
 def attention_temporal(q, k, v, heads, head_dim, out=None):
     """q/k/v [f, npix, heads*head_dim] views (frame-major) of one video, or [b, f, npix, heads*head_dim] for b videos back
     to back (one launch): attention over the f tokens of each pixel."""
