@@ -65,10 +65,12 @@ def build(verbose: bool = True) -> Path:
         objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
     newest = max(o.stat().st_mtime for o in objs)
     if (not LIB.exists()) or LIB.stat().st_mtime < newest:
-        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
+        tmp = LIB.with_suffix(".so.tmp")          # link aside, then rename: a reader never sees a half-written library
+        cmd = [NVCC, *ARCH, "-shared", "-o", str(tmp), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     if verbose:
         print(f"[build] {LIB} ({LIB.stat().st_size // 1024} KiB, {len(objs)} objects)")
     return LIB

@@ -13,16 +13,18 @@
 // MUFU cycles per block).
 //
 //   warps 0-3  softmax / output (thread r <-> TMEM lane r)
-//   warp 4     TMA producer: Q (8 chunks, once), then per key block 8 K chunks through a 4-slot ring and the two
-//              128-column halves of the V block through 2 slots
+//   warp 4     TMA producer for Q (8 chunks, once) and K: 8 chunks per key block through a 6-slot ring
 //   warp 5     tcgen05.mma issue; S is double-buffered in TMEM so QK(j+1) runs under the softmax of block j
+//   warp 6     TMA producer for V: the two 128-column halves of a block through 2 slots.  K and V have their OWN producers:
+//              V(j)'s slot frees only when PV(j-1) has run, i.e. after the softmax of block j-1, and an in-order producer
+//              that blocks there holds back K(j+1) -- measured 6 000 cycles per block against 1 536 cycles of MMA work
 // TMEM columns: S0 [0,64)  S1 [64,128)  O [128,384).
 #include "common.h"
 #include "ptx.cuh"
 
 namespace vg {
 
-static constexpr int kT5Threads = 192;
+static constexpr int kT5Threads = 224;
 static constexpr int kT5D = 512;
 static constexpr int kT5Chunks = kT5D / 64;        // 8 channel chunks of 64
 static constexpr int kT5Half = 256;                // output columns per CTA
@@ -32,7 +34,7 @@ static constexpr int kT5QChunkBytes = kT5TileQ * 64 * 2;   // 16 KB
 static constexpr int kT5KChunkBytes = kT5TileK * 64 * 2;   // 8 KB
 static constexpr int kT5VSlotBytes = kT5TileK * 128 * 2;   // 16 KB: 64 keys x 128 channels = two 64-channel sub-blocks
 static constexpr int kT5PBytes = kT5TileQ * kT5TileK * 2;  // 16 KB
-static constexpr int kT5KSlots = 4;
+static constexpr int kT5KSlots = 6;
 static constexpr float kT5Rescale = 8.0f;
 
 struct alignas(64) Attn512Params {
@@ -46,24 +48,23 @@ struct alignas(64) Attn512Params {
 };
 
 __global__ void __launch_bounds__(kT5Threads, 1) attn_d512_sm100_kernel(const __grid_constant__ Attn512Params p) {
-  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                     // 8 x 16 KB
-  uint8_t* sK = sQ + kT5Chunks * kT5QChunkBytes;          // 4 x 8 KB
+  uint8_t* sK = sQ + kT5Chunks * kT5QChunkBytes;          // 6 x 8 KB
   uint8_t* sV = sK + kT5KSlots * kT5KChunkBytes;          // 2 x 16 KB
   uint8_t* sP = sV + 2 * kT5VSlotBytes;                   // 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kT5PBytes);
-  uint64_t* q_full = bars;          // [1]
-  uint64_t* k_full = bars + 1;      // [4]
-  uint64_t* k_empty = bars + 5;     // [4]
-  uint64_t* v_full = bars + 9;      // [2]
-  uint64_t* v_empty = bars + 11;    // [2]
-  uint64_t* s_full = bars + 13;     // [2] per S buffer
-  uint64_t* s_free = bars + 15;     // [2] per S buffer: scores are in registers
-  uint64_t* p_full = bars + 17;     // [1] P(j) in shared memory, O rescaled
-  uint64_t* o_full = bars + 18;     // [1] PV(j) finished: P buffer free, O readable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* q_full = bars;                       // [1]
+  uint64_t* k_full = bars + 1;                   // [kT5KSlots]
+  uint64_t* k_empty = k_full + kT5KSlots;        // [kT5KSlots]
+  uint64_t* v_full = k_empty + kT5KSlots;        // [2]
+  uint64_t* v_empty = v_full + 2;                // [2]
+  uint64_t* s_full = v_empty + 2;                // [2] per S buffer
+  uint64_t* s_free = s_full + 2;                 // [2] per S buffer: scores are in registers
+  uint64_t* p_full = s_free + 2;                 // [1] P(j) in shared memory, O rescaled
+  uint64_t* o_full = p_full + 1;                 // [1] PV(j) finished: P buffer free, O readable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kT5TileQ, half = blockIdx.y, batch = blockIdx.z;
@@ -95,27 +96,31 @@ __global__ void __launch_bounds__(kT5Threads, 1) attn_d512_sm100_kernel(const __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer: Q once, then the K chunk ring
     if (elect_one()) {
       mbar_expect_tx(q_full, kT5Chunks * kT5QChunkBytes);
       for (int c = 0; c < kT5Chunks; ++c) tma_load_3d(sQ + c * kT5QChunkBytes, &p.map_q, q_full, c * 64, q0, batch);
     }
     __syncwarp();
+    int slot = 0, use = 0;                   // ring position; `use` = how many times this slot has been filled before
     for (int j = 0; j < nkv; ++j) {
       for (int c = 0; c < kT5Chunks; ++c) {
-        const int kc = j * kT5Chunks + c, slot = kc & (kT5KSlots - 1);
-        if (kc >= kT5KSlots) mbar_wait(&k_empty[slot], ((kc >> 2) - 1) & 1, 30);
+        if (use > 0) mbar_wait(&k_empty[slot], (use - 1) & 1, 30);
         if (elect_one()) {
           mbar_expect_tx(&k_full[slot], kT5KChunkBytes);
           tma_load_3d(sK + slot * kT5KChunkBytes, &p.map_k, &k_full[slot], c * 64, j * kT5TileK, batch);
         }
         __syncwarp();
+        if (++slot == kT5KSlots) { slot = 0; ++use; }
       }
-      for (int h = 0; h < 2; ++h) {   // V slot h: channels [half*256 + h*128, +128) as two 64-channel sub-blocks
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ TMA producer: V halves (slot h)
+    for (int j = 0; j < nkv; ++j) {
+      for (int h = 0; h < 2; ++h) {   // channels [half*256 + h*128, +128) as two 64-channel sub-blocks
         if (j >= 1) mbar_wait(&v_empty[h], (j - 1) & 1, 31);
         if (elect_one()) {
           mbar_expect_tx(&v_full[h], kT5VSlotBytes);
@@ -132,11 +137,12 @@ __global__ void __launch_bounds__(kT5Threads, 1) attn_d512_sm100_kernel(const __
     const uint32_t idesc_pv = umma_idesc_f16(kT5TileQ, 64, 0, 1);         // 128 x 64, B (= V) MN-major
     const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
     const uint32_t t_o = tmem + 128;
+    int kslot = 0, kuse = 0;
     auto issue_qk = [&](int j) {
       const uint32_t t_s = tmem + (j & 1) * 64;
       for (int c = 0; c < kT5Chunks; ++c) {
-        const int kc = j * kT5Chunks + c, slot = kc & (kT5KSlots - 1);
-        mbar_wait(&k_full[slot], (kc >> 2) & 1, 32);
+        const int slot = kslot;
+        mbar_wait(&k_full[slot], kuse & 1, 32);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a_desc = umma_desc_sw128(q_addr + c * kT5QChunkBytes, 16, 1024);
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(kT5Threads, 1) attn_d512_sm100_kernel(const __
           if (c == kT5Chunks - 1) umma_commit(&s_full[j & 1]);
         }
         __syncwarp();
+        if (++kslot == kT5KSlots) { kslot = 0; ++kuse; }
       }
     };
     mbar_wait(q_full, 0, 33);
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(kT5Threads, 1) attn_d512_sm100_kernel(const __
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ------------------------------------------------------------------ softmax / output warps
     const int r = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -335,7 +342,7 @@ extern "C" int vgen_attention_d512(const void* q, const void* k, const void* v, 
   p.lq = (int)lq;
   p.lk = (int)lk;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t smem = kT5Chunks * kT5QChunkBytes + kT5KSlots * kT5KChunkBytes + 2 * kT5VSlotBytes + kT5PBytes + 20 * 8 + 16 + 1024;
+  const size_t smem = kT5Chunks * kT5QChunkBytes + kT5KSlots * kT5KChunkBytes + 2 * kT5VSlotBytes + kT5PBytes + (2 * kT5KSlots + 12) * 8 + 16 + 1024;
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(attn_d512_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

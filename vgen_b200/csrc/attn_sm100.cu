@@ -52,18 +52,27 @@ struct alignas(64) AttnParams {
   int lq, lk, heads;
   int kv_batch_div;   // kv batch index = batch / kv_batch_div (context shared by the frames of a video)
   float scale_log2;   // softmax scale * log2(e)
+  int tcsum;          // timing twin only: which variant to instrument
   long long* timing;  // kTiming only: per-phase cycle counters of one CTA's two softmax warps (tools/bench_attn.py)
 };
 
-template <bool kTiming>
+// kTcSum: the softmax row sums are taken by the TENSOR CORE: the PV product runs with N = 80 instead of 64, the 16 extra
+// columns of "V" being a constant shared-memory atom whose first column is 1.0 (the second MN-atom of the B descriptor, reached
+// through its leading-byte-offset), so O[:, 64] accumulates sum_k P[r, k] in fp32 -- exactly the normaliser of the fp16 P the
+// product used.  That removes one dependent FADD per exponential from the softmax warps (the FMA pipe shares issue slots
+// with the MUFU-bound exponentials) at the cost of 25 % more PV tensor time, which has slack (tensor pipe 33 % busy).
+template <bool kTiming, bool kTcSum>
 __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
+  constexpr int kOCols = kTcSum ? 80 : 64;     // TMEM columns of one q-tile's O accumulator
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 2 x 16 KB
   uint8_t* sK = sQ + 2 * kQBytes;                      // 2 x 16 KB
   uint8_t* sV = sK + kKvStages * kKBytes;              // 2 x 16 KB
   uint8_t* sP = sV + kKvStages * kKBytes;              // 2 tiles x 2 buffers x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kPBytes);
+  uint8_t* sOnes = sP + 4 * kPBytes;                    // kTcSum: 2 KB constant MN-major atom (16 keys x 64 columns, column 0 = 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (kTcSum ? 2048 : 0));
+  if (kTcSum && (reinterpret_cast<uintptr_t>(smem) - reinterpret_cast<uintptr_t>(smem_raw)) > 832) __trap();  // launcher's slack
   uint64_t* q_full = bars;            // [1]
   uint64_t* k_full = bars + 1;        // [2]
   uint64_t* k_empty = bars + 3;       // [2] both tiles' QK(j) finished
@@ -107,11 +116,20 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
     tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
+  if (kTcSum && warp < 4) {
+    // rows = keys (two 8-row groups 1024 B apart, like the V tile), 128 B per row, 128B-swizzled: the 16-byte piece holding
+    // column 0 of row r sits at piece index (0 ^ (r & 7))
+    const int t = threadIdx.x;                       // 128 threads x 16 B = 2 KB
+    const int row = t >> 3, piece = t & 7;
+    const uint32_t val = (piece == (row & 7)) ? 0x00003C00u : 0u;   // fp16 1.0 in the low half
+    st_shared_v4(smem_u32(sOnes) + t * 16, val, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+kOCols) O1 [256+kOCols, 256+2*kOCols)
 
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
@@ -143,10 +161,11 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
     // ------------------------------------------------------------------ MMA issue for q-tile i (warp-uniform loop)
     const int i = warp - 9;
     const uint32_t idesc_qk = umma_idesc_f16(kTileQ, kTileK, 0, 0);
-    const uint32_t idesc_pv = umma_idesc_f16(kTileQ, kD, 0, 1);  // B (= V) is MN-major
+    const uint32_t idesc_pv = umma_idesc_f16(kTileQ, kOCols, 0, 1);  // B (= V [+ the ones atom]) is MN-major
+    const uint32_t ones_addr = smem_u32(sOnes);
     const uint32_t q_addr = smem_u32(sQ) + i * kQBytes, k_addr = smem_u32(sK), v_addr0 = smem_u32(sV);
     const uint32_t p_addr0 = smem_u32(sP) + 2 * i * kPBytes;
-    const uint32_t t_s = tmem + i * 128, t_o = tmem + 256 + i * 64;
+    const uint32_t t_s = tmem + i * 128, t_o = tmem + 256 + i * kOCols;
     // Event-driven issue: QK(j+1) goes out as soon as the softmax warps of this tile have pulled S(j) into registers
     // (s_free), i.e. it overlaps their exponentials; PV(j) goes out when P(j) is in shared memory.
     // Per tile the events arrive in a fixed order -- s_free(j) (scores in registers) always precedes p_full(j) (P
@@ -183,7 +202,9 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
           // A: P chunk (ks/4) of 64 keys, 16-key step (ks%4) inside the 128B swizzle row
           const uint64_t a_desc = umma_desc_sw128(p_addr + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 16, 1024);
           // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart
-          const uint64_t b_desc = umma_desc_sw128(v_addr + ks * 16 * 128, 1024, 1024);
+          // (kTcSum: the second 64-column atom of B is the ones tile: leading byte offset = its distance from this K step)
+          const uint32_t vk = v_addr + ks * 16 * 128;
+          const uint64_t b_desc = umma_desc_sw128(vk, kTcSum ? ones_addr - vk : 1024u, 1024);
           umma_f16_ss(t_o, a_desc, b_desc, idesc_pv, (j | ks) != 0);  // O accumulates over blocks
         }
         umma_commit(&o_full[2 * i + (j & 1)]);
@@ -198,7 +219,7 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
     const int r = q * 32 + lane;      // row within the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t t_s = tmem + i * 128 + lane_base;
-    const uint32_t t_o = tmem + 256 + i * 64 + lane_base;
+    const uint32_t t_o = tmem + 256 + i * kOCols + lane_base;
     const uint32_t prow0 = smem_u32(sP + 2 * i * kPBytes + r * 128);
     const int sw = r & 7;
     const float sl2 = p.scale_log2;
@@ -258,6 +279,14 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
             for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
             tmem_st32(t_o + c, o);
           }
+          if (kTcSum) {       // the row-sum column (and its 15 zero companions) rescales with O
+            uint32_t o16[16];
+            tmem_ld16(t_o + kD, o16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) o16[t] = __float_as_uint(__uint_as_float(o16[t]) * alpha);
+            tmem_st16(t_o + kD, o16);
+          }
           tmem_st_wait();
           tmem_ld32(t_s + 0, s0);
           tmem_ld32(t_s + 32, s1);
@@ -296,7 +325,7 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
       float e[8];                                                                            \
       _Pragma("unroll") for (int t = 0; t < 8; ++t) {                                        \
         e[t] = fast_exp2(fmaf(__uint_as_float(ARR[g * 8 + t]), sl2, neg_ms));                \
-        LSUM += e[t];                                                                        \
+        if (!kTcSum) LSUM += e[t];                                                           \
       }                                                                                      \
       const int piece = (((C0) & 63) >> 3) + g; /* 16-byte piece inside the 128 B row */     \
       st_shared_v4(chunk + ((piece ^ sw) << 4), pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), \
@@ -324,6 +353,12 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
     mbar_wait(&o_full[2 * i + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1, 22);
     tc_fence_after();
     const int row = q0 + i * kTileQ + r;
+    if (kTcSum) {
+      uint32_t o16[16];
+      tmem_ld16(t_o + kD, o16);
+      tmem_ld_wait();
+      l_run = __uint_as_float(o16[0]);
+    }
     const float inv_l = 1.0f / l_run;
     __half* orow = p.out + (long)batch * p.out_batch_stride + (long)row * p.ldo + head * kD;
     uint32_t oa[32], ob[32];
@@ -355,13 +390,15 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __grid_constant__ AttnParams p) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
-  attn_sm100_body<false>(p);
+  attn_sm100_body<false, false>(p);
+}
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_tcsum_kernel(const __grid_constant__ AttnParams p) {
+  attn_sm100_body<false, true>(p);
 }
 // instrumented twin (phase cycle counters); only tools/bench_attn.py launches it (vgen_attention_d64_debug)
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_timing_kernel(const __grid_constant__ AttnParams p) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
-  attn_sm100_body<true>(p);
+  if (p.tcsum) attn_sm100_body<true, true>(p);
+  else attn_sm100_body<true, false>(p);
 }
 
 }  // namespace vg
@@ -411,15 +448,25 @@ static int attention_d64_impl(const void* q, const void* k, const void* v, void*
   p.kv_batch_div = (int)kv_batch_div;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.timing = timing;
-  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 22 * 8 + 16 + 1024;
+  static int tcsum_mode = -1;   // VGEN_ATTN_TCSUM=0 keeps the row sums in the softmax warps (A/B knob, read once)
+  if (tcsum_mode < 0) {
+    const char* e = getenv("VGEN_ATTN_TCSUM");
+    tcsum_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  p.tcsum = tcsum_mode;
+  // tcsum: + 2 KB ones atom; the 1024-byte alignment slack shrinks to 832 so the total stays within 227 KB (the kernel traps
+  // if the dynamic shared memory base is ever less aligned than that)
+  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 22 * 8 + 16 + (tcsum_mode ? 2048 + 832 : 1024);
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.mark();
   }
   dim3 grid((unsigned)cdiv(lq, 2 * kTileQ), (unsigned)heads, (unsigned)batch);
   if (timing) launch_kernel(attn_sm100_timing_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (tcsum_mode) launch_kernel(attn_sm100_tcsum_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
   else launch_kernel(attn_sm100_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
   VG_LAUNCH_CHECK("attn_sm100_kernel");
   return 0;

@@ -40,7 +40,6 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __half* __rest
                                                             long seq_stride_q, long tok_stride_o, long seq_stride_o,
                                                             float scale_log2, long spb, long batch_stride_q,
                                                             long batch_stride_o) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   constexpr int kRow = 72;  // halfs per smem row
   constexpr int MT = LP / 16;
   extern __shared__ __align__(16) __half sm_t[];
@@ -191,7 +190,6 @@ __global__ void attn_small_kernel(const __half* __restrict__ q, const __half* __
                                   __half* __restrict__ out, long nseq, int heads, int L, int d, long tok_stride,
                                   long seq_stride, long tok_stride_o, long seq_stride_o, float scale, long spb,
                                   long batch_stride, long batch_stride_o) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nseq * heads * L) return;
   const int i = (int)(idx % L);

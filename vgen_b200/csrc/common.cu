@@ -25,15 +25,6 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 const std::string& last_error() { return g_last_error; }
 
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VGEN_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
 int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);

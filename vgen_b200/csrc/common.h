@@ -53,13 +53,10 @@ extern std::atomic<long long> g_launches;  // kernels launched by this library (
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
-// Every kernel of the library is launched through this: cudaLaunchKernelEx with programmatic dependent launch (PDL).
-// A forward is ~1 200 back-to-back kernels on one stream; with PDL the next kernel's CTAs are scheduled -- and run their
-// prologue (barrier init, TMEM allocation, descriptor prefetch, index math) -- while the previous kernel drains, and block in
-// `griddepcontrol.wait` (pdl_wait() in ptx.cuh) before they touch global memory.  The edges survive stream capture, so
-// the CUDA-graphed forwards keep them.  VGEN_PDL=0 launches without the attribute (the device-side instructions are
-// no-ops then).
-bool pdl_enabled();
+// Every kernel of the library is launched through this (cudaLaunchKernelEx; one place to add launch attributes).
+// Programmatic dependent launch was tried here in round 2 and removed: inside the CUDA-graphed forwards it bought nothing
+// (config 2: 243.7 vs 241.1 ms/step, VideoLCM 16.40 vs 16.49) and the early-started kernels produced WRONG results in this
+// chain (eager and replayed forwards differed by up to 2.7 with it, bit-identical without: profiles/r02f_pdl_determinism.md).
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -69,11 +66,8 @@ static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -15,7 +15,6 @@ __device__ __forceinline__ float silu_e(float v) { return __fdividef(v, 1.0f + _
 // the result leaves as fp16 [b, c, f, h, w] (:276).  Inside, everything is channels-last.
 template <typename Tin>
 __global__ void cp_to_pc_kernel(const Tin* __restrict__ x, __half* __restrict__ y, long n, int c, long p, int c_pad) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * p * c_pad) return;
   const int ci = (int)(idx % c_pad);
@@ -27,7 +26,6 @@ __global__ void cp_to_pc_kernel(const Tin* __restrict__ x, __half* __restrict__ 
 }
 template <typename Tout>
 __global__ void pc_to_cp_kernel(const __half* __restrict__ x, Tout* __restrict__ y, long n, int c, long p, long ldx) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * p * c) return;
   const long pi = idx % p;
@@ -49,7 +47,6 @@ __global__ void pc_to_cp_kernel<__half>(const __half* __restrict__ x, __half* __
 // out[(n,oy,ox)][(ky*kw+kx)*c + ci] = act(x[n][oy*s-pt+ky][ox*s-pl+kx][ci]); columns >= kh*kw*c are zero.
 __global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__ out, long nimg, int h, int w, int c,
                               int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int kpad, int act_silu) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const bool vec = (c % 8 == 0);
   const int kv = vec ? kpad / 8 : kpad;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,7 +94,6 @@ __global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__
 
 // ------------------------------------------------------------------ nearest x2 upsample (channels-last)
 __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nimg, int h, int w, int c8) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = nimg * (2L * h) * (2L * w) * c8;
   if (idx >= total) return;
@@ -113,7 +109,6 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 // ------------------------------------------------------------------ 2-D strided copy (channel concat)
 __global__ void copy2d_kernel(const __half* __restrict__ src, long lds, __half* __restrict__ dst, long ldd, long rows,
                               int cols) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const bool vec = (cols % 8 == 0) && (lds % 8 == 0) && (ldd % 8 == 0) &&
                    (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,7 +130,6 @@ __global__ void copy2d_kernel(const __half* __restrict__ src, long lds, __half* 
 // op: 0 silu(a)  1 a+b  2 gelu(a) (erf)  3 a*s  4 a + s*b
 __global__ void eltwise_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ y, long n,
                                int op, float s) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const float x = __half2float(a[idx]);
@@ -155,7 +149,6 @@ __global__ void eltwise_kernel(const __half* __restrict__ a, const __half* __res
 __global__ void linear_small_kernel(const __half* __restrict__ a, long lda, const __half* __restrict__ w,
                                     const float* __restrict__ bias, const __half* __restrict__ res, long ldr,
                                     __half* __restrict__ out, long ldo, long m, int n, int k, int silu_in, int gelu_out) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long warp_id = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_id >= m * n) return;
@@ -184,7 +177,6 @@ __global__ void linear_small_kernel(const __half* __restrict__ a, long lda, cons
 __global__ void linear_tinyk_kernel(const __half* __restrict__ a, long lda, const __half* __restrict__ w,
                                     const float* __restrict__ bias, const __half* __restrict__ res, long ldr,
                                     __half* __restrict__ out, long ldo, long m, int n, int k, int silu_in, int gelu_out) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m * n) return;
   const long mi = idx / n;
@@ -207,7 +199,6 @@ __global__ void linear_tinyk_kernel(const __half* __restrict__ a, long lda, cons
 // ------------------------------------------------------------------ sinusoidal embedding
 // tools/modules/unet/util.py:178-190: outer(t, 10000^(-i/half)), cat[cos, sin]; fp32 math, fp16 store
 __global__ void sinusoidal_kernel(const float* __restrict__ t, __half* __restrict__ out, int b, int dim) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (idx >= b * half) return;
@@ -220,7 +211,6 @@ __global__ void sinusoidal_kernel(const float* __restrict__ t, __half* __restric
 
 // ------------------------------------------------------------------ row softmax (in place, fp16 rows)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long ld, int n, float scale) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   __shared__ float red[8];
   __half* row = x + (long)blockIdx.x * ld;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -248,7 +238,6 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 // ------------------------------------------------------------------ adaptive average pool (channels-last)
 __global__ void adaptive_avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nimg, int h, int w, int c,
                                         int oh, int ow, int silu_in) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nimg * oh * ow * c) return;
   const int ci = (int)(idx % c);
@@ -279,7 +268,6 @@ struct DdimCoef {
 __global__ void ddim_step_kernel(float* __restrict__ xt, const __half* __restrict__ y, const __half* __restrict__ u,
                                  const float* __restrict__ noise, long n, float guide, int has_u, DdimCoef k, int mean_v,
                                  float* __restrict__ x0_out) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float out;
@@ -310,7 +298,6 @@ __global__ void ddim_step_kernel(float* __restrict__ xt, const __half* __restric
 // fp32 in the reference layout [n][zc][p].
 __global__ void vae_sample_kernel(const __half* __restrict__ mom, const float* __restrict__ noise, float* __restrict__ z,
                                   long n, int zc, long p, float scale) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * zc * p) return;
   const long pi = idx % p;

@@ -53,7 +53,6 @@ __device__ __forceinline__ void acc8(const uint4& u, float (&s)[8], float (&q)[8
 
 template <int VPT>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, float2* __restrict__ partial, GnGeom g) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   extern __shared__ float sm[];  // [2][rows][C]
   const int n = blockIdx.y, sp = blockIdx.x;
   const int tid = threadIdx.x;
@@ -127,7 +126,6 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
 // one warp per group: lanes stride over the splits, then a shuffle tree of Chan merges
 __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats,
                                                            GnGeom g, float eps) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int n = blockIdx.x;
   const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float cnt = 0.f, mean = 0.f, m2 = 0.f;
@@ -199,7 +197,6 @@ template <int VPT>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                        const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, GnGeom g, int silu, long apply_chunk) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
   const int r = tid / g.cols, cv = tid - r * g.cols;
@@ -270,7 +267,6 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long rows, int C, long ldx, long ldy, float eps) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const int lane = threadIdx.x & 31;
   const int C8 = C >> 3;
   const long warps_total = (long)gridDim.x * (blockDim.x >> 5);
@@ -363,7 +359,6 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 long rows, int C, long ldx, long ldy, float eps) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   constexpr int RW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, li = lane % LPR;
@@ -451,7 +446,6 @@ __global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __
 __global__ void layernorm_small_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, long rows, int C,
                                        long ldx, long ldy, float eps) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const __half* xr = x + row * ldx;

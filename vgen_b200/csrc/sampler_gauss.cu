@@ -14,7 +14,6 @@ namespace vg {
 
 __global__ void cfg_combine_kernel(const __half* __restrict__ y, const __half* __restrict__ u, __half* __restrict__ out,
                                    long n_per, float g, double* __restrict__ stats) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long b = blockIdx.y;
   const __half* yb = y + b * n_per;
   const __half* ub = u + b * n_per;
@@ -55,7 +54,6 @@ __global__ void cfg_combine_kernel(const __half* __restrict__ y, const __half* _
 __global__ void gauss_x0_kernel(const float* __restrict__ xt, const __half* __restrict__ out, const double* __restrict__ stats,
                                 float guide_rescale, float alpha, float sigma, int pred, float* __restrict__ x0, long n_per,
                                 long total) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   float o = __half2float(out[idx]);
@@ -83,7 +81,6 @@ __global__ void gauss_x0_kernel(const float* __restrict__ xt, const __half* __re
 __global__ void lincomb_f32_kernel(float* __restrict__ out, long n, const float* __restrict__ x0, float a0,
                                    const float* __restrict__ x1, float a1, const float* __restrict__ x2, float a2,
                                    const float* __restrict__ x3, float a3) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float r = a0 * x0[idx];

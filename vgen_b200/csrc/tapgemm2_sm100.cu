@@ -40,7 +40,6 @@ struct alignas(64) TapGemm2Params {
 template <bool kGeglu>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     tapgemm_sm100_2cta_kernel(const __grid_constant__ TapGemm2Params p) {
-  pdl_launch_dependents();   // PDL: the next kernel's CTAs may be scheduled as this grid's CTAs retire
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -91,7 +90,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  pdl_wait();   // prologue (barriers, TMEM, descriptor prefetch) overlapped the previous kernel; its outputs are needed from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {

@@ -12,7 +12,6 @@ __device__ __forceinline__ float gelu_erf_s(float x) { return 0.5f * x * (1.0f +
 
 __global__ void tapgemm_simt_kernel(const __half* __restrict__ A, long st1, long st2, long st3,
                                     const __half* __restrict__ W, TapGemmShape s, TapGemmEpilogue e) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long rows = (long)s.d1 * s.d2 * s.d3;
   const int out_n = e.geglu ? s.n / 2 : s.n;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;

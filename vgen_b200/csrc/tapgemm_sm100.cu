@@ -50,7 +50,6 @@ struct alignas(64) TapGemmKernelParams {
 
 template <bool kGeglu>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid_constant__ TapGemmKernelParams p) {
-  pdl_launch_dependents();   // PDL: the next kernel's CTAs may be scheduled as this grid's CTAs retire
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment is required by the 128B swizzle atom (8 rows x 128 B).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,7 +97,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();   // prologue overlapped the previous kernel; its outputs are needed from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {

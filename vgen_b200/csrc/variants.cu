@@ -19,7 +19,6 @@ __global__ void attn_cross_small_kernel(const __half* __restrict__ q, const __ha
                                         const __half* __restrict__ v, __half* __restrict__ out, long batch, int heads,
                                         int lq, int lk, int d, long ldq, long ldk, long ldv, long ldo, int kv_batch_div,
                                         float scale) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= batch * heads * lq) return;
@@ -70,7 +69,6 @@ __global__ void attn_cross_small_kernel(const __half* __restrict__ q, const __ha
 // middle axis: src = (dst + 0.5) * lin/lout - 0.5 clamped at 0, neighbours clamped at lin-1.
 __global__ void interp_linear_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nseq, int lin, int lout,
                                           int c) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nseq * lout * c) return;
   const int ch = (int)(idx % c);
@@ -96,7 +94,6 @@ constexpr int kFfSlices = 4;
 __global__ void __launch_bounds__(kFfChan* kFfSlices)
     fourier_lowfreq_kernel(const __half* __restrict__ x, __half* __restrict__ y, int h, int w, int c, long ldx, long ldy,
                            float scale) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   extern __shared__ float sm[];
   float* cy = sm;            // cos(2 pi y / h)
   float* sy = cy + h;
@@ -153,7 +150,6 @@ __global__ void __launch_bounds__(kFfChan* kFfSlices)
 // the first and last row, util.py:799-801); 8 channels per thread.
 __global__ void upsample2x_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y, long nimg, int h, int w, int cv,
                                        int row0, int rows_out) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = nimg * rows_out * (2L * w) * cv;
   if (idx >= total) return;
@@ -167,7 +163,6 @@ __global__ void upsample2x_rows_kernel(const __half* __restrict__ x, __half* __r
 
 __global__ void scale_copy2d_kernel(const __half* __restrict__ src, long lds, __half* __restrict__ dst, long ldd, long rows,
                                     int cols, float s) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   const long r = idx / cols;

@@ -24,7 +24,6 @@ __device__ __forceinline__ unsigned to_u8(float x, float sd, float mn) {
 __global__ void __launch_bounds__(256) video_to_rgb8_kernel(const float* __restrict__ vid, uint8_t* __restrict__ out,
                                                             unsigned long long* __restrict__ band, int C, long F, long HW,
                                                             float m0, float m1, float m2, float s0, float s1, float s2) {
-  pdl_entry();   // PDL: dependents may be scheduled; no global access before the prerequisite grid completed
   // grid.y = frame; x over groups of 4 pixels
   const long f = blockIdx.y;
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
