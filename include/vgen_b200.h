@@ -147,12 +147,20 @@ int vgen_vae_sample(const void* moments, const float* noise, float* z, int64_t n
 
 /* ---- model-variant prologues (variants.cu) -------------------------- */
 /* softmax(q k^T * scale) v for any head_dim <= 256 and ragged (lq, lk); same addressing as
- * vgen_attention_d64.  Serves the 16-token context transformer of UNetSD_HiGen (head_dim 160).
+ * vgen_attention_d64.  Serves the 16-token context transformer of UNetSD_HiGen (head_dim 160) and the CLIP towers
+ * (77 causal text tokens, head_dim 64; 257 image tokens, head_dim 80).
  * replaces: CrossAttention / memory_efficient_attention inside TextContextCrossTransformerMultiLayer,
  * unet_higen.py:154-172 (BasicTransformerBlock util.py:674-741) */
 int vgen_attention_cross_small(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
                                int64_t lq, int64_t lk, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv,
-                               int64_t ldo, int64_t kv_batch_div, float scale, void* stream);
+                               int64_t ldo, int64_t kv_batch_div, int causal, float scale, void* stream);
+/* CLIP conditioning (clip_embedder.py:183-212 on open_clip's CLIP): causal = 1 above is the text tower's attn_mask.
+ * out[r][:] = fp16(table[ids[r]][:] + pos[r % L][:]) -- token_embedding(text) + positional_embedding (:190-191) */
+int vgen_embed_tokens(const int64_t* ids, const float* table, const float* pos, void* out, int64_t nrows, int64_t L,
+                      int64_t W, int64_t vocab, void* stream);
+/* x[b][i] = fp16(x[b][i] + add[i]), i < n: "x = x + self.positional_embedding" of the vision tower
+ * (utils/reward/open_clip/transformer.py VisionTransformer.forward) */
+int vgen_add_rows_f32(void* x, const float* add, int64_t batch, int64_t n, void* stream);
 /* F.interpolate(x.transpose(1,2), size=lout, mode='linear').transpose(1,2) on x[nseq][lin][c] fp16
  * (motion embedding, unet_higen.py:389-392) */
 int vgen_interp_linear_rows(const void* x, void* y, int64_t nseq, int64_t lin, int64_t lout, int64_t c, void* stream);

@@ -272,3 +272,33 @@ def test_cuda_graph_replay_matches_eager(golden_dir, name, monkeypatch):
     monkeypatch.setenv("VGEN_CUDA_GRAPH", "1")
     m.load_state_dict({k: v * 1.01 for k, v in m.state_dict().items()}, strict=True)
     assert not graph.stats(m), "repacking the weights must drop the captured graphs"
+
+
+def test_clip_towers_parity(golden_dir):
+    """the CLIP text / image towers behind the reference's FrozenOpenCLIP*Embedder classes, against
+    outputs frozen from the reference's vendored open_clip model (fp32): tokens of both `layer` settings, pooled text
+    embedding, image embedding.  fp16 activations vs an fp32 reference: relative L2 within 3e-3."""
+    from oracle.make_golden_clip import TINY
+    from vgen_b200 import clip
+    g = np.load(os.path.join(golden_dir, "clip_tiny.npz"))
+    spec = [(k, tuple(s)) for k, s in json.load(open(os.path.join(golden_dir, "clip_tiny.spec.json")))]
+    sd = synth.state_dict([s for s in spec if len(s[1]) > 0], seed=31)
+    for k in ("positional_embedding", "visual.positional_embedding", "visual.class_embedding", "token_embedding.weight"):
+        sd[k] = synth.tensor(k, dict(spec)[k], 0.02, 31)
+    sd["logit_scale"] = torch.tensor(2.6592)
+    tokens = torch.from_numpy(g["tokens"]).cuda()
+    image = synth.tensor("clip_image", (2, 3, 56, 56), 1.0, 31).cuda()
+    for layer in ("last", "penultimate"):
+        e = clip.FrozenOpenCLIPTextVisualEmbedder(None, arch=TINY, layer=layer)
+        e.model.load_state_dict(sd, strict=True)
+        e.model.cuda()
+        xt, x = e.model.encode_text(tokens, e.layer_idx)
+        xt2, x2 = e.model.encode_text(tokens, e.layer_idx)            # second call: CUDA-graph replay
+        assert torch.equal(x, x2) and x.dtype == torch.float32 and x.shape == (7, 77, 128)
+        e_x, e_xt = _rel_l2(x, torch.from_numpy(g[f"{layer}_x"]).cuda()), _rel_l2(xt, torch.from_numpy(g[f"{layer}_xt"]).cuda())
+        print(f"clip text {layer}: tokens {e_x:.3e}, pooled {e_xt:.3e}")
+        assert e_x < 3e-3 and e_xt < 3e-3
+    xi = e.model.encode_image(image)
+    e_xi = _rel_l2(xi, torch.from_numpy(g["xi"]).cuda())
+    print(f"clip image: {e_xi:.3e}")
+    assert e_xi < 3e-3 and xi.shape == (2, 64)

@@ -337,3 +337,33 @@ def test_fastdiv_multiply_shift_is_exact():
         assert mul < (1 << 32)
         q = xs if d == 1 else ((xs * np.uint64(mul)) >> np.uint64(32)) >> np.uint64(shr)
         assert np.array_equal(q, xs // np.uint64(d)), d
+
+
+def test_clip_spec_and_tokenizer(golden_dir):
+    """CLIP conditioning host side: parameter spec == open_clip's CLIP.state_dict() (names, shapes, order), embedders are
+    registered, and -- index work, bit-exact -- tokenizer ids == the ids the reference's vendored tokenizer produced
+    (tests/golden/clip_tiny.npz); live comparison on more strings when the reference (and its merge list) is mounted."""
+    from oracle.make_golden_clip import PROMPTS, TINY
+    from vgen_b200 import clip, clip_tokenizer as ct, registry
+    spec = [(k, tuple(s)) for k, s in json.load(open(os.path.join(golden_dir, "clip_tiny.spec.json")))]
+    assert clip.clip_spec(TINY) == spec
+    full = clip.clip_spec(clip.ARCHS["ViT-H-14"])
+    assert len(full) == 686 and sum(int(np.prod(s)) for _, s in full) == 986109441      # open_clip ViT-H-14
+    vgen_b200.register(force_local=True)
+    assert {"FrozenOpenCLIPEmbedder", "FrozenOpenCLIPVisualEmbedder", "FrozenOpenCLIPTextVisualEmbedder"} <= set(registry.EMBEDDER.class_map)
+    e = clip.FrozenOpenCLIPTextVisualEmbedder(None, arch=TINY, layer="penultimate")
+    assert e.layer_idx == 1 and all(k.startswith("model.") for k in e.state_dict()) and len(e.state_dict()) == len(spec)
+    assert not any(p.requires_grad for p in e.parameters())
+    with pytest.raises(lib.VgenError):
+        e.model.text_tokens(torch.zeros(1, 77, dtype=torch.long))              # CPU: no fallback
+    try:
+        sys.path.insert(0, "/root/reference")
+        ct.find_bpe_file()
+    except FileNotFoundError:
+        pytest.skip("CLIP merge list not available on this box (it ships with open_clip / the reference tree)")
+    g = np.load(os.path.join(golden_dir, "clip_tiny.npz"))
+    assert np.array_equal(ct.tokenize(PROMPTS).numpy(), g["tokens"])
+    from oracle.make_golden_clip import load_reference_open_clip
+    _, tok_mod = load_reference_open_clip()
+    extra = ["", "naive cafe 42", "a " * 200, "UPPER lower MiXeD", "tab\tand\nnewline", "emoji \U0001F680 \u65e5\u672c\u8a9e"]
+    assert torch.equal(ct.tokenize(extra), tok_mod.tokenize(extra))

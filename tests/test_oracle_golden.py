@@ -133,3 +133,23 @@ def test_video_oracle_matches_reference_frames(golden_dir):
         assert len(frames) == gold.shape[0], name
         assert np.array_equal(np.stack(frames), gold), name
     assert g["grey_last_frames"].shape[0] == int(g["grey_last_nframes_in"]) - 1
+
+
+def test_clip_oracle_matches_reference_golden(golden_dir):
+    """oracle/clip_oracle.py vs outputs frozen from the reference's vendored open_clip CLIP driven like
+    tools/modules/clip_embedder.py:183-212 (tests/golden/clip_tiny.npz, oracle/make_golden_clip.py)."""
+    from oracle import clip_oracle as co
+    from oracle.make_golden_clip import TINY
+    g = np.load(os.path.join(golden_dir, "clip_tiny.npz"))
+    spec = [(k, tuple(s)) for k, s in json.load(open(os.path.join(golden_dir, "clip_tiny.spec.json")))]
+    sd = synth.state_dict([s for s in spec if len(s[1]) > 0], seed=31)
+    for k in ("positional_embedding", "visual.positional_embedding", "visual.class_embedding", "token_embedding.weight"):
+        sd[k] = synth.tensor(k, dict(spec)[k], 0.02, 31)
+    tokens = torch.from_numpy(g["tokens"])
+    image = synth.tensor("clip_image", (2, 3, 56, 56), 1.0, 31)
+    for layer in ("last", "penultimate"):
+        xt, x = co.encode_text(sd, tokens, TINY["text_cfg"]["heads"], layer)
+        assert float((xt - torch.from_numpy(g[f"{layer}_xt"])).abs().max()) < 1e-4 * float(np.abs(g[f"{layer}_xt"]).max())
+        assert float((x - torch.from_numpy(g[f"{layer}_x"])).abs().max()) < 1e-4 * float(np.abs(g[f"{layer}_x"]).max())
+    xi = co.encode_image(sd, image, TINY["vision_cfg"]["head_width"])
+    assert float((xi - torch.from_numpy(g["xi"])).abs().max()) < 1e-4 * float(np.abs(g["xi"]).max())

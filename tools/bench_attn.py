@@ -26,8 +26,12 @@ def call(q, k, v, out, h, div, timing=None):
 def main():
     g = torch.Generator().manual_seed(0)
     res = []
-    for (b, h, lq, lk, div) in [(32, 5, 14080, 14080, 1), (32, 10, 3520, 3520, 1), (32, 20, 880, 880, 1), (32, 20, 220, 220, 1),
-                                (32, 5, 14080, 145, 16), (32, 10, 3520, 145, 16)]:
+    only = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--only" else None
+    shapes = [(32, 5, 14080, 14080, 1), (32, 10, 3520, 3520, 1), (32, 20, 880, 880, 1), (32, 20, 220, 220, 1),
+              (32, 5, 14080, 145, 16), (32, 10, 3520, 145, 16)]
+    if only is not None:
+        shapes = [] if only == "d512" else [shapes[int(only)]]
+    for (b, h, lq, lk, div) in shapes:
         inner = h * 64
         if lq == lk and div == 1:
             qkv = torch.randn(b, lq, 3 * inner, generator=g).half().cuda()
@@ -64,7 +68,7 @@ def main():
             print(json.dumps(row), flush=True)
             res.append(row)
     from vgen_b200 import ops
-    for (b, l) in [(2, 14080), (4, 14400), (2, 1792)]:
+    for (b, l) in ([(2, 14080), (4, 14400), (2, 1792)] if only in (None, "d512") else []):
         qkv = torch.randn(b, l, 1536, generator=g).half().cuda()
         q, k, v = qkv[:, :, :512], qkv[:, :, 512:1024], qkv[:, :, 1024:]
         out = torch.empty(b, l, 512, device="cuda", dtype=torch.float16)

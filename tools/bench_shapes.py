@@ -23,6 +23,8 @@ def main():
              ("linear", 14080, 1280, 1280, True, False), ("conv", 16, 88, 160, 320, 320), ("conv", 16, 22, 40, 1280, 1280), ("conv", 16, 11, 20, 1280, 1280),
              ("tconv", 16, 14080, 320, 320)]
     out = []
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":       # ncu captures: one case, few iterations
+        cases = [cases[int(sys.argv[2])]]
     for c in cases:
         if c[0] == "linear":
             _, m, k, n, res, geglu = c

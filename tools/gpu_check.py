@@ -289,6 +289,31 @@ def group_attention():
             report(f"attention_temporal f{f_} npix{npix} h{heads} d{d}", rel_err(out, ref), 3e-3)
         run_case(f"tattn {f_} {npix}", f)
 
+    for (b, heads, L, d) in [(3, 2, 77, 64), (1, 16, 77, 64), (2, 2, 17, 80)]:
+        def f():
+            inner = heads * d
+            qkv = rnd(b, L, 3 * inner).half()
+            q, k, v = qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:]
+            out = ops.attention_cross_small(q, k, v, heads, causal=True)
+            torch.cuda.synchronize()
+            sp = lambda t: t.float().reshape(b, L, heads, d).permute(0, 2, 1, 3)  # noqa: E731
+            ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), is_causal=True).permute(0, 2, 1, 3).reshape(b, L, inner)
+            report(f"attention_cross_small causal b{b} h{heads} L{L} d{d}", rel_err(out, ref), 3e-3)
+        run_case(f"causal attn {b} {heads} {L}", f)
+
+    def f():
+        ids = torch.randint(0, 1000, (3, 77), generator=g).cuda()
+        table, pos = rnd(1000, 128, scale=0.02), rnd(77, 128, scale=0.02)
+        out = ops.embed_tokens(ids, table, pos)
+        x = rnd(4, 17, 160).half()
+        add = rnd(17, 160)
+        ref2 = (x.float() + add).half()
+        ops.add_rows_f32_(x, add)
+        torch.cuda.synchronize()
+        report("embed_tokens", rel_err(out, (table[ids] + pos).half()), 1e-6)
+        report("add_rows_f32", rel_err(x, ref2), 1e-6)
+    run_case("clip embeddings", f)
+
     def f():
         x = rnd(700, 1500, scale=3.0).half()
         ref = torch.softmax(x.float() * 0.25, dim=-1)

@@ -7,7 +7,11 @@ import torch  # noqa: E402
 from vgen_b200 import ops  # noqa: E402
 
 g = torch.Generator().manual_seed(0)
-for (n, p, c, silu) in [(16, 14080, 640, True), (1, 225280, 320, True), (16, 14080, 320, True), (1, 56320, 640, True), (1, 14080, 1280, True), (16, 880, 1280, True)]:
+only = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--only" else None
+gn_cases = [(16, 14080, 640, True), (1, 225280, 320, True), (16, 14080, 320, True), (1, 56320, 640, True), (1, 14080, 1280, True), (16, 880, 1280, True)]
+if only is not None:
+    gn_cases = [] if only == "ln" else [gn_cases[int(only)]]
+for (n, p, c, silu) in gn_cases:
     x = torch.randn(n, p, c, generator=g).half().cuda()
     ga, be = torch.randn(c, generator=g).cuda(), torch.randn(c, generator=g).cuda()
     y = torch.empty_like(x)
@@ -26,7 +30,7 @@ for (n, p, c, silu) in [(16, 14080, 640, True), (1, 225280, 320, True), (16, 140
     ms = ts[2]
     print({"shape": (n, p, c), "ms": round(ms, 4), "GBs_rw": round(4.0 * x.numel() / ms / 1e6, 1), "GBs_3pass": round(6.0 * x.numel() / ms / 1e6, 1)}, flush=True)
 
-for (rows, c) in [(450560, 320), (112640, 640), (28160, 1280)]:
+for (rows, c) in ([(450560, 320), (112640, 640), (28160, 1280)] if only is None else ([(450560, 320)] if only == "ln" else [])):
     x = torch.randn(rows, c, generator=g).half().cuda()
     ga, be = torch.randn(c, generator=g).cuda(), torch.randn(c, generator=g).cuda()
     y = torch.empty_like(x)

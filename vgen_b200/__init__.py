@@ -23,6 +23,9 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name in ("GaussianDiffusion", "DiffusionDDIMSR"):
         from . import diffusion_gauss
         return getattr(diffusion_gauss, name)
+    if name in ("FrozenOpenCLIPEmbedder", "FrozenOpenCLIPVisualEmbedder", "FrozenOpenCLIPTextVisualEmbedder"):
+        from . import clip
+        return getattr(clip, name)
     if name == "LCMScheduler":
         from .lcm import LCMScheduler
         return LCMScheduler

@@ -61,7 +61,21 @@ struct alignas(64) AttnParams {
 // through its leading-byte-offset), so O[:, 64] accumulates sum_k P[r, k] in fp32 -- exactly the normaliser of the fp16 P the
 // product used.  That removes one dependent FADD per exponential from the softmax warps (the FMA pipe shares issue slots
 // with the MUFU-bound exponentials) at the cost of 25 % more PV tensor time, which has slack (tensor pipe 33 % busy).
-template <bool kTiming, bool kTcSum>
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.5e-5 -- six times below
+// the fp16 rounding P receives): x = n + f with n = round(x), f in [-0.5, 0.5]; the integer part is added into the exponent.
+// kPoly = k routes every k-th exponential of a row through this instead of MUFU.EX2, whose pipe (16 / clk / SM) bounds the
+// kernel; with the row sums on the tensor core (kTcSum) the FMA pipe has the room.
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;                  // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05517146f, 0.24261086f);
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992809f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <bool kTiming, bool kTcSum, int kPoly>
 __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
   constexpr int kOCols = kTcSum ? 80 : 64;     // TMEM columns of one q-tile's O accumulator
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -324,7 +338,8 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
     _Pragma("unroll") for (int g = 0; g < 4; ++g) {                                          \
       float e[8];                                                                            \
       _Pragma("unroll") for (int t = 0; t < 8; ++t) {                                        \
-        e[t] = fast_exp2(fmaf(__uint_as_float(ARR[g * 8 + t]), sl2, neg_ms));                \
+        const float xa = fmaf(__uint_as_float(ARR[g * 8 + t]), sl2, neg_ms);                 \
+        e[t] = (kPoly > 0 && (t % (kPoly > 0 ? kPoly : 1)) == kPoly - 1) ? exp2_poly3(xa) : fast_exp2(xa); \
         if (!kTcSum) LSUM += e[t];                                                           \
       }                                                                                      \
       const int piece = (((C0) & 63) >> 3) + g; /* 16-byte piece inside the 128 B row */     \
@@ -390,15 +405,16 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __grid_constant__ AttnParams p) {
-  attn_sm100_body<false, false>(p);
+  attn_sm100_body<false, false, 0>(p);
 }
+template <int kPoly>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_tcsum_kernel(const __grid_constant__ AttnParams p) {
-  attn_sm100_body<false, true>(p);
+  attn_sm100_body<false, true, kPoly>(p);
 }
 // instrumented twin (phase cycle counters); only tools/bench_attn.py launches it (vgen_attention_d64_debug)
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_timing_kernel(const __grid_constant__ AttnParams p) {
-  if (p.tcsum) attn_sm100_body<true, true>(p);
-  else attn_sm100_body<true, false>(p);
+  if (p.tcsum) attn_sm100_body<true, true, 0>(p);
+  else attn_sm100_body<true, false, 0>(p);
 }
 
 }  // namespace vg
@@ -454,19 +470,31 @@ static int attention_d64_impl(const void* q, const void* k, const void* v, void*
     tcsum_mode = (e && e[0] == '0') ? 0 : 1;
   }
   p.tcsum = tcsum_mode;
+  static int poly_mode = -1;    // VGEN_ATTN_POLY=k: every k-th exponential on the FMA pipe (0 = all on MUFU); tcsum only
+  if (poly_mode < 0) {
+    const char* e = getenv("VGEN_ATTN_POLY");
+    poly_mode = e ? atoi(e) : 0;
+    if (poly_mode != 2 && poly_mode != 4 && poly_mode != 8) poly_mode = 0;
+  }
   // tcsum: + 2 KB ones atom; the 1024-byte alignment slack shrinks to 832 so the total stays within 227 KB (the kernel traps
   // if the dynamic shared memory base is ever less aligned than that)
   const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 22 * 8 + 16 + (tcsum_mode ? 2048 + 832 : 1024);
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.mark();
   }
   dim3 grid((unsigned)cdiv(lq, 2 * kTileQ), (unsigned)heads, (unsigned)batch);
   if (timing) launch_kernel(attn_sm100_timing_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
-  else if (tcsum_mode) launch_kernel(attn_sm100_tcsum_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (tcsum_mode && poly_mode == 2) launch_kernel(attn_sm100_tcsum_kernel<2>, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (tcsum_mode && poly_mode == 4) launch_kernel(attn_sm100_tcsum_kernel<4>, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (tcsum_mode && poly_mode == 8) launch_kernel(attn_sm100_tcsum_kernel<8>, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (tcsum_mode) launch_kernel(attn_sm100_tcsum_kernel<0>, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
   else launch_kernel(attn_sm100_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
   VG_LAUNCH_CHECK("attn_sm100_kernel");
   return 0;

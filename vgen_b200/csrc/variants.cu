@@ -18,7 +18,7 @@ namespace vg {
 __global__ void attn_cross_small_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
                                         const __half* __restrict__ v, __half* __restrict__ out, long batch, int heads,
                                         int lq, int lk, int d, long ldq, long ldk, long ldv, long ldo, int kv_batch_div,
-                                        float scale) {
+                                        float scale, int causal) {
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= batch * heads * lq) return;
@@ -37,7 +37,9 @@ __global__ void attn_cross_small_kernel(const __half* __restrict__ q, const __ha
     acc[c] = 0.f;
   }
   float mx = -INFINITY, l = 0.f;
-  for (int j = 0; j < lk; ++j) {
+  // causal (CLIP text tower, attn_mask of open_clip's build_attention_mask): query i sees keys 0 .. i + (lk - lq)
+  const int jend = causal ? min(lk, i + 1 + (lk - lq)) : lk;
+  for (int j = 0; j < jend; ++j) {
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -174,14 +176,41 @@ __global__ void scale_copy2d_kernel(const __half* __restrict__ src, long lds, __
 
 using namespace vg;
 
+// ------------------------------------------------------------------ CLIP embeddings (clip_embedder.py:190-191)
+// out[r][:] = fp16(table[ids[r]][:] + pos[r % L][:]): token_embedding(text) + positional_embedding, fp32 like the
+// reference, rounded once.  One thread per 4 channels.
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                    const float* __restrict__ pos, __half* __restrict__ out, long nrows, int L, int W, long vocab) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w4 = W >> 2;
+  if (idx >= nrows * w4) return;
+  const long r = idx / w4;
+  const int c = (int)(idx - r * w4) * 4;
+  long id = ids[r];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(table + id * W + c));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(pos + (r % L) * W + c));
+  uint2 o;
+  o.x = pack_half2(a.x + b.x, a.y + b.y);
+  o.y = pack_half2(a.z + b.z, a.w + b.w);
+  *reinterpret_cast<uint2*>(out + r * W + c) = o;
+}
+// x[b][i] = fp16(float(x[b][i]) + add[i]) for i < n: the vision tower's positional embedding broadcast over the batch
+__global__ void add_rows_f32_kernel(__half* __restrict__ x, const float* __restrict__ add, long batch, long n) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * n) return;
+  x[idx] = __float2half_rn(__half2float(x[idx]) + add[idx % n]);
+}
+
 static inline unsigned nblk(long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
 
 extern "C" {
 
 int vgen_attention_cross_small(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
                                int64_t lq, int64_t lk, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                               int64_t kv_batch_div, float scale, void* stream) {
+                               int64_t kv_batch_div, int causal, float scale, void* stream) {
   VG_REQUIRE(q && k && v && out, "vgen_attention_cross_small: null pointer");
+  VG_REQUIRE(!causal || lk >= lq, "vgen_attention_cross_small: causal needs lk >= lq");
   VG_REQUIRE(batch >= 0 && heads > 0 && lq > 0 && lk > 0 && head_dim > 0 && head_dim <= 256 && kv_batch_div > 0 &&
                  batch % kv_batch_div == 0,
              "vgen_attention_cross_small: bad shape");
@@ -190,7 +219,7 @@ int vgen_attention_cross_small(const void* q, const void* k, const void* v, void
   launch_kernel(attn_cross_small_kernel, dim3(nblk(warps * 32, 128)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(k), reinterpret_cast<const __half*>(v),
       reinterpret_cast<__half*>(out), batch, (int)heads, (int)lq, (int)lk, (int)head_dim, ldq, ldk, ldv, ldo,
-      (int)kv_batch_div, scale);
+      (int)kv_batch_div, scale, causal ? 1 : 0);
   VG_LAUNCH_CHECK("attn_cross_small_kernel");
   return 0;
 }
@@ -240,6 +269,27 @@ int vgen_scale_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int6
   launch_kernel(scale_copy2d_kernel, dim3(nblk(rows * cols, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(src), lds, reinterpret_cast<__half*>(dst), ldd, rows, (int)cols, s);
   VG_LAUNCH_CHECK("scale_copy2d_kernel");
+  return 0;
+}
+
+int vgen_embed_tokens(const int64_t* ids, const float* table, const float* pos, void* out, int64_t nrows, int64_t L, int64_t W,
+                      int64_t vocab, void* stream) {
+  VG_REQUIRE(ids && table && pos && out && nrows >= 0 && L > 0 && W > 0 && W % 4 == 0 && vocab > 0, "vgen_embed_tokens: bad arguments");
+  VG_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(pos)) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 7) == 0, "vgen_embed_tokens: table / pos must be 16-byte aligned");
+  if (nrows == 0) return 0;
+  launch_kernel(embed_tokens_kernel, dim3(nblk(nrows * (W / 4), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                reinterpret_cast<const long long*>(ids), table, pos, reinterpret_cast<__half*>(out), nrows, (int)L, (int)W, vocab);
+  VG_LAUNCH_CHECK("embed_tokens_kernel");
+  return 0;
+}
+
+int vgen_add_rows_f32(void* x, const float* add, int64_t batch, int64_t n, void* stream) {
+  VG_REQUIRE(x && add && batch >= 0 && n > 0, "vgen_add_rows_f32: bad arguments");
+  if (batch == 0) return 0;
+  launch_kernel(add_rows_f32_kernel, dim3(nblk(batch * n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                reinterpret_cast<__half*>(x), add, batch, n);
+  VG_LAUNCH_CHECK("add_rows_f32_kernel");
   return 0;
 }
 

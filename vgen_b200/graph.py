@@ -122,11 +122,11 @@ def graphed(fn):
     """Decorator for a SpecModule method whose tensor arguments fully determine its device work."""
     @functools.wraps(fn)
     def wrapper(self, *args, **kwargs):
+        W = self._packed
+        if W is None:                                    # not packed yet (or just invalidated): eager call packs (or raises on CPU)
+            return fn(self, *args, **kwargs)
         if (not enabled() or ops.PROF is not None or not getattr(self, "use_cuda_graph", True)
                 or torch.cuda.is_current_stream_capturing()):
-            return fn(self, *args, **kwargs)
-        W = self._packed
-        if W is None:                                    # not packed yet (or just invalidated): eager call packs
             return fn(self, *args, **kwargs)
         cache = W.get("__graphs__")
         if cache is None:

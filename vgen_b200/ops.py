@@ -325,8 +325,9 @@ def attention_temporal(q, k, v, heads, head_dim, out=None):
     return out4[0] if squeeze else out4
 
 
-def attention_cross_small(q, k, v, heads, kv_batch_div=1, out=None):
-    """q [b, lq, heads*d], k/v [b // kv_batch_div, lk, heads*d] for any d <= 256 (tiny problems only)."""
+def attention_cross_small(q, k, v, heads, kv_batch_div=1, out=None, causal=False):
+    """q [b, lq, heads*d], k/v [b // kv_batch_div, lk, heads*d] for any d <= 256 (tiny problems only); causal: query i
+    attends keys 0 .. i + (lk - lq) (the CLIP text tower's mask)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _chk16(t, nm)
         if t.dim() != 3 or t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
@@ -339,7 +340,7 @@ def attention_cross_small(q, k, v, heads, kv_batch_div=1, out=None):
     if out is None:
         out = torch.empty(b, lq, inner, device=q.device, dtype=torch.float16)
     rc = _l.load().vgen_attention_cross_small(_p(q), _p(k), _p(v), _p(out), b, heads, lq, lk, d, q.stride(1), k.stride(1),
-                                              v.stride(1), out.stride(1), kv_batch_div, d ** -0.5, _stream())
+                                              v.stride(1), out.stride(1), kv_batch_div, 1 if causal else 0, d ** -0.5, _stream())
     _l.check(rc, "vgen_attention_cross_small")
     return out
 
@@ -604,3 +605,30 @@ def video_to_rgb8(video, mean, std, want_band=True):
               lambda: _l.load().vgen_video_to_rgb8(_p(video), c, f, h, w, m3, s3, _p(out), _p(band), _stream()))
     _l.check(rc, "vgen_video_to_rgb8")
     return out, band
+
+
+def embed_tokens(ids, table, pos):
+    """ids int64 [b, L] (CUDA), table fp32 [vocab, W], pos fp32 [L, W] -> fp16 [b, L, W] = table[ids] + pos."""
+    if ids.dtype != torch.int64 or not ids.is_cuda or not ids.is_contiguous() or ids.dim() != 2:
+        raise _l.VgenError("embed_tokens: ids must be a contiguous CUDA int64 tensor [b, L]")
+    for t, nm in ((table, "table"), (pos, "pos")):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise _l.VgenError(f"embed_tokens: {nm} must be a contiguous CUDA fp32 tensor")
+    b, L = ids.shape
+    vocab, W = table.shape
+    if pos.shape != (L, W):
+        raise _l.VgenError("embed_tokens: pos must be [L, W]")
+    out = torch.empty(b, L, W, device=ids.device, dtype=torch.float16)
+    rc = _l.load().vgen_embed_tokens(_p(ids), _p(table), _p(pos), _p(out), b * L, L, W, vocab, _stream())
+    _l.check(rc, "vgen_embed_tokens")
+    return out
+
+
+def add_rows_f32_(x, add):
+    """x fp16 [b, ...] += add fp32 [...] broadcast over the leading dim, in place."""
+    _chk16(x, "x")
+    if not x.is_contiguous() or add.dtype != torch.float32 or not add.is_contiguous() or add.numel() * x.shape[0] != x.numel():
+        raise _l.VgenError("add_rows_f32_: x must be contiguous fp16 [b, n...] and add contiguous fp32 [n...]")
+    rc = _l.load().vgen_add_rows_f32(_p(x), _p(add), x.shape[0], add.numel(), _stream())
+    _l.check(rc, "vgen_add_rows_f32")
+    return x

@@ -53,24 +53,28 @@ class Registry:
         return _register
 
 
-MODEL = DIFFUSION = AUTO_ENCODER = None
+MODEL = DIFFUSION = AUTO_ENCODER = EMBEDDER = None
 USING_REFERENCE_REGISTRY = False
 
 
 def register(force_local: bool = False):
-    """Register the UNets (T2VBase, I2VGen, VideoLCM, SR600, HiGen), DiffusionDDIM and AutoencoderKL under the
-    reference's registry names.  Returns the three registries."""
-    global MODEL, DIFFUSION, AUTO_ENCODER, USING_REFERENCE_REGISTRY
+    """Register the UNets (T2VBase, I2VGen, VideoLCM, SR600, HiGen), DiffusionDDIM(SR), AutoencoderKL and the three
+    FrozenOpenCLIP*Embedder classes under the reference's registry names.  Returns (MODEL, DIFFUSION, AUTO_ENCODER); the
+    embedder registry is `vgen_b200.registry.EMBEDDER`."""
+    global MODEL, DIFFUSION, AUTO_ENCODER, EMBEDDER, USING_REFERENCE_REGISTRY
     from .autoencoder import AutoencoderKL
+    from .clip import FrozenOpenCLIPEmbedder, FrozenOpenCLIPTextVisualEmbedder, FrozenOpenCLIPVisualEmbedder
     from .diffusion import DiffusionDDIM
     from .diffusion_gauss import DiffusionDDIMSR
     from .unet import UNetSD_HiGen, UNetSD_I2VGen, UNetSD_SR600, UNetSD_T2VBase, UNetSD_VideoLCM
 
     regs = None
+    emb = None
     if not force_local:
         try:
             from utils.registry_class import AUTO_ENCODER as A, DIFFUSION as D, MODEL as M  # the reference's singletons
             regs = (M, D, A)
+            from utils.registry_class import EMBEDDER as emb  # noqa: N811
             USING_REFERENCE_REGISTRY = True
         except ImportError:  # the reference is not on sys.path: use the local mirror (tests, bench)
             regs = None
@@ -87,4 +91,7 @@ def register(force_local: bool = False):
         DIFFUSION.register_class()(DiffusionDDIM)
         DIFFUSION.register_class()(DiffusionDDIMSR)
         AUTO_ENCODER.register_class()(AutoencoderKL)
+        EMBEDDER = emb if emb is not None else (EMBEDDER or Registry("EMBEDDER"))   # also reachable as vgen_b200.registry.EMBEDDER
+        for cls in (FrozenOpenCLIPEmbedder, FrozenOpenCLIPVisualEmbedder, FrozenOpenCLIPTextVisualEmbedder):
+            EMBEDDER.register_class()(cls)
     return MODEL, DIFFUSION, AUTO_ENCODER
