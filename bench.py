@@ -628,7 +628,7 @@ def main():
     vae = None
     if not args.no_decode:
         vae = build_vae(AUTO_ENCODER, dev)
-        decode_video(vae, xt[:, :, :2 * wl["decode_chunk"]], wl["decode_chunk"])     # warm-up + graph capture
+        decode_video(vae, xt[:, :, :3 * wl["decode_chunk"]], wl["decode_chunk"])     # warm-up: pack, sighting, graph capture
         nfr = min(wl["decode_frames"], xt.shape[2])
         dms, img = timed(lambda: decode_video(vae, xt[:, :, :nfr], wl["decode_chunk"]), dev, parallel)
         decode = {"frames_per_s": world * nfr / (dms / 1e3), "ms": dms, "frames": nfr, "frame_hw": list(wl["frame_hw"]),

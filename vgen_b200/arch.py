@@ -7,8 +7,8 @@ builds its module tree:
     tools/modules/unet/unet_t2v.py:87-208, unet_i2vgen.py:88-240 (block layout),
     tools/modules/unet/util.py:311-353,674-741,807-898,1189-1238,1652-1684 (per-module parameters),
     tools/modules/autoencoder.py:30-62,276-313,338-363,483-547,581-651 (VAE).
-tests/test_arch_spec.py pins the generated spec against tests/golden/*.spec.json (dumped from the
-reference classes by oracle/make_golden.py).
+tests/test_host_logic.py::test_param_spec_equals_reference pins the generated spec against
+tests/golden/*.spec.json (dumped from the reference classes by oracle/make_golden.py).
 """
 from __future__ import annotations
 

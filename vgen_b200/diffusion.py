@@ -6,8 +6,9 @@ Host side (kept in fp64 torch / Python exactly like the reference, so it is bit-
   * beta schedules `cosine`, `linear_sd` (+ zero-terminal-SNR rescale)     schedules.py:5-21,62-63,72-79,143-165
   * cumulative-product tables                                             diffusion_ddim.py:46-78
   * the timestep list  (1 + arange(0, T, T // S)).clamp(0, T-1).flip(0)   diffusion_ddim.py:250
-Only the sampling entry points used by the inference engines are provided (ddim_sample_loop,
-ddim_sample, p_mean_variance for var_type fixed_small / mean_type v|eps); the training losses, PLMS and
+Only the sampling entry points used by the inference engines are provided: ddim_sample_loop and ddim_sample for
+var_type fixed_small / mean_type v|eps.  The arithmetic of the reference's p_mean_variance (:147-206: two model calls,
+CFG mix, v -> x0) has no method of its own here -- it lives inside the fused step kernel; the training losses, PLMS and
 reward variants are out of scope and absent (calling them raises AttributeError, not a fallback).
 """
 from __future__ import annotations

@@ -124,7 +124,13 @@ def graphed(fn):
     def wrapper(self, *args, **kwargs):
         W = self._packed
         if W is None:                                    # not packed yet (or just invalidated): eager call packs (or raises on CPU)
-            return fn(self, *args, **kwargs)
+            out = fn(self, *args, **kwargs)
+            if self._packed is not None and enabled():   # it still counts as the first sighting of this signature
+                flat = GraphCache._flatten(args, kwargs)
+                if flat is not None:
+                    c = self._packed.setdefault("__graphs__", {}).setdefault(fn.__name__, GraphCache())
+                    c.seen[flat[1]] = max(c.seen.get(flat[1], 0), 1)
+            return out
         if (not enabled() or ops.PROF is not None or not getattr(self, "use_cuda_graph", True)
                 or torch.cuda.is_current_stream_capturing()):
             return fn(self, *args, **kwargs)
