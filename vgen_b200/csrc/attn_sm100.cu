@@ -61,7 +61,11 @@ struct alignas(64) AttnParams {
 // through its leading-byte-offset), so O[:, 64] accumulates sum_k P[r, k] in fp32 -- exactly the normaliser of the fp16 P the
 // product used.  That removes one dependent FADD per exponential from the softmax warps (the FMA pipe shares issue slots
 // with the MUFU-bound exponentials) at the cost of 25 % more PV tensor time, which has slack (tensor pipe 33 % busy).
-template <bool kTiming, bool kTcSum>
+// kAlt: the two q-tiles take turns in the exponential phase (A0 B0 A1 B1 ...) through a token barrier, so one tile's TMEM
+// load / max / barrier round trips hide under the other's exponentials, which then have the MUFU pipe to themselves.
+// Without kTcSum a lone warp managed only 12.2 cycles per exponential (the dependent FADD chain) and alternation lost
+// (profiles/r02d_attn_alternation.json); it is re-measured on top of the tensor-core row sums.
+template <bool kTiming, bool kTcSum, bool kAlt = false>
 __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
   constexpr int kOCols = kTcSum ? 80 : 64;     // TMEM columns of one q-tile's O accumulator
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -72,7 +76,7 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
   uint8_t* sP = sV + kKvStages * kKBytes;              // 2 tiles x 2 buffers x 32 KB
   uint8_t* sOnes = sP + 4 * kPBytes;                    // kTcSum: 2 KB constant MN-major atom (16 keys x 64 columns, column 0 = 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (kTcSum ? 2048 : 0));
-  if (kTcSum && (reinterpret_cast<uintptr_t>(smem) - reinterpret_cast<uintptr_t>(smem_raw)) > 832) __trap();  // launcher's slack
+  if (kTcSum && (reinterpret_cast<uintptr_t>(smem) - reinterpret_cast<uintptr_t>(smem_raw)) > 816) __trap();  // launcher's slack
   uint64_t* q_full = bars;            // [1]
   uint64_t* k_full = bars + 1;        // [2]
   uint64_t* k_empty = bars + 3;       // [2] both tiles' QK(j) finished
@@ -82,7 +86,8 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
   uint64_t* p_full = bars + 11;       // [2][2] per q-tile and P buffer: P(j) in smem, S(j) consumed, O rescaled
   uint64_t* o_full = bars + 15;       // [2][2] per q-tile and P buffer: PV(j) finished (buffer j&1 free, O readable)
   uint64_t* s_free = bars + 19;       // [2] per q-tile: S(j) is in registers, QK(j+1) may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* turn = bars + 21;         // [2] kAlt: the other q-tile has finished the exponentials of a block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
   // (one barrier per P buffer: the softmax warps may publish P(j+1) before the MMA warp has looked at P(j), and a
   // single barrier two phases ahead of its observer aliases)
 
@@ -109,6 +114,7 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
       mbar_init(&o_full[2 * i], 1);
       mbar_init(&o_full[2 * i + 1], 1);
       mbar_init(&s_free[i], 4);
+      mbar_init(&turn[i], 4);
     }
     fence_mbar_init();
   }
@@ -313,6 +319,10 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
       if (kTiming) { tm_c0 = clock64(); tm_ldmax += tm_c0 - tm_c1; }
       // P buffer j&1 was last read by PV(j-2)
       if (j >= 2) mbar_wait(&o_full[2 * i + (j & 1)], ((j >> 1) - 1) & 1, 23);
+      if (kAlt) {   // tile 0 goes first; tile 1's block j follows tile 0's block j, tile 0's block j+1 follows tile 1's block j
+        if (i == 0) { if (j > 0) mbar_wait(&turn[0], (j - 1) & 1, 24); }
+        else mbar_wait(&turn[1], j & 1, 25);
+      }
       if (kTiming) { tm_c1 = clock64(); tm_wait_p += tm_c1 - tm_c0; }
       const uint32_t prow = prow0 + (j & 1) * kPBytes;
       const float neg_ms = -m_ref * sl2;
@@ -343,6 +353,7 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[2 * i + (j & 1)]);
+      if (kAlt && lane == 0) mbar_arrive(&turn[1 - i]);
       if (kTiming) tm_exp += clock64() - tm_c1;
     }
     if (kTiming && p.timing && q == 0 && lane == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
@@ -394,6 +405,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_kernel(const __gri
 }
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_tcsum_kernel(const __grid_constant__ AttnParams p) {
   attn_sm100_body<false, true>(p);
+}
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_tcsum_alt_kernel(const __grid_constant__ AttnParams p) {
+  attn_sm100_body<false, true, true>(p);
 }
 // instrumented twin (phase cycle counters); only tools/bench_attn.py launches it (vgen_attention_d64_debug)
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_sm100_timing_kernel(const __grid_constant__ AttnParams p) {
@@ -454,18 +468,25 @@ static int attention_d64_impl(const void* q, const void* k, const void* v, void*
     tcsum_mode = (e && e[0] == '0') ? 0 : 1;
   }
   p.tcsum = tcsum_mode;
-  // tcsum: + 2 KB ones atom; the 1024-byte alignment slack shrinks to 832 so the total stays within 227 KB (the kernel traps
+  static int alt_mode = -1;     // VGEN_ATTN_ALT=1: alternate the q-tiles' exponential phases (A/B knob, read once; tcsum only)
+  if (alt_mode < 0) {
+    const char* e = getenv("VGEN_ATTN_ALT");
+    alt_mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  // tcsum: + 2 KB ones atom; the 1024-byte alignment slack shrinks to 816 so the total stays within 227 KB (the kernel traps
   // if the dynamic shared memory base is ever less aligned than that)
-  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 22 * 8 + 16 + (tcsum_mode ? 2048 + 832 : 1024);
+  const size_t smem = 2 * kQBytes + kKvStages * 2 * kKBytes + 4 * kPBytes + 24 * 8 + 16 + (tcsum_mode ? 2048 + 816 : 1024);
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(attn_sm100_tcsum_alt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VG_CUDA(cudaFuncSetAttribute(attn_sm100_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.mark();
   }
   dim3 grid((unsigned)cdiv(lq, 2 * kTileQ), (unsigned)heads, (unsigned)batch);
   if (timing) launch_kernel(attn_sm100_timing_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (tcsum_mode && alt_mode && lk >= 4 * kTileK) launch_kernel(attn_sm100_tcsum_alt_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
   else if (tcsum_mode) launch_kernel(attn_sm100_tcsum_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
   else launch_kernel(attn_sm100_kernel, dim3(grid), dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream), p);
   VG_LAUNCH_CHECK("attn_sm100_kernel");
