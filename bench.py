@@ -429,15 +429,45 @@ def timed(fn, dev, parallel):
     return parallel.max_over_ranks(e0.elapsed_time(e1), dev), r
 
 
-def decode_video(vae, lat, chunk):
+def decode_video(vae, lat, chunk, keep=False):
     """video_data = latents / scale_factor; chunks of decoder_bs frames through AutoencoderKL.decode
-    (inference_i2vgen_entrance.py:222-230)."""
+    (inference_i2vgen_entrance.py:222-230).  keep: return all frames as [1, 3, f, H, W] (the tensor the engines hand to
+    save_i2vgen_video_safe) instead of the last chunk."""
     z = (lat / 0.18215)[0].permute(1, 0, 2, 3).contiguous()
     z = torch.nan_to_num(z).clamp(-10, 10)         # random-weight latents may blow up; values are irrelevant for timing
-    out = None
+    out, frames = None, []
     for i in range(0, z.shape[0], chunk):
         out = vae.decode(z[i:i + chunk])
+        if keep:
+            frames.append(out)
+    if keep:
+        return torch.cat(frames, dim=0).permute(1, 0, 2, 3).unsqueeze(0).contiguous()
     return out
+
+
+def write_out_video(frames):
+    """Frames to bytes to file through the drop-in writer (vgen_b200.video_io, utils/video_op.py:167-213): device kernel +
+    pinned D2H timed with CUDA events, the encoder (ffmpeg pipe or OpenCV) with the host clock."""
+    import tempfile
+
+    from vgen_b200 import video_io
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    host, band, ev = video_io.frames_to_host(frames, [0.5] * 3, [0.5] * 3)
+    e1.record()
+    ev.synchronize()
+    torch.cuda.synchronize()
+    n = video_io.select_frames(host, band)
+    res = {"frames": int(n), "bytes_d2h": int(host.numel()), "ms_kernel_plus_d2h": e0.elapsed_time(e1)}
+    t0 = time.perf_counter()
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            path = video_io._encode(os.path.join(td, "bench.mp4"), host[:n].numpy(), 8)
+            res["file_bytes"] = os.path.getsize(path)
+        res["ms_encode_host"] = (time.perf_counter() - t0) * 1e3
+    except Exception as e:  # noqa: BLE001 - no encoder on the box: the bytes still left the GPU
+        res["encode_error"] = repr(e)[:160]
+    return res
 
 
 def ops_lincomb(terms):
@@ -520,7 +550,7 @@ class Stepper:
             vae.decode((spat.squeeze(2) / 0.18215).clamp(-10, 10))
             kw = [dict(k, spat_prior=torch.nan_to_num(spat.squeeze(2)).clamp(-10, 10)) for k in self.kw]
             lat = self.diff.ddim_sample_loop(c["noise"].clone(), self.model, kw, guide_scale=12.0, ddim_timesteps=50, eta=0.0)
-        return lat, decode_video(vae, lat, wl["decode_chunk"])
+        return lat, decode_video(vae, lat, wl["decode_chunk"], keep=True)
 
 
 def main():
@@ -643,7 +673,9 @@ def main():
             stepper.full_video(vae)                  # cheap: warm once so the timed prompt replays graphs
         fms, (lat, frames) = timed(lambda: stepper.full_video(vae), dev, parallel)
         nfr = wl["decode_frames"] + (1 if args.workload == "higen" else 0)
+        wo = write_out_video(frames)
         full = {"videos_per_s": world / (fms / 1e3), "s_per_video": fms / 1e3, "frames_per_s_e2e": world * nfr / (fms / 1e3),
+                "write_out": wo,
                 "prompts": world, "finite": bool(torch.isfinite(lat).all()),
                 "what": {"i2vgen": "50 CFG DDIM steps + 16-frame decode", "videolcm": "4 LCM steps + 16-frame decode (8 chunks x 2)",
                          "sr600": "30 DDIM-inversion steps + 30 DPM-Solver++(2M) SDE CFG steps + 32-frame decode",

@@ -74,10 +74,14 @@ def register(force_local: bool = False):
         try:
             from utils.registry_class import AUTO_ENCODER as A, DIFFUSION as D, MODEL as M  # the reference's singletons
             regs = (M, D, A)
-            from utils.registry_class import EMBEDDER as emb  # noqa: N811
             USING_REFERENCE_REGISTRY = True
         except ImportError:  # the reference is not on sys.path: use the local mirror (tests, bench)
             regs = None
+        if regs is not None:
+            try:
+                from utils.registry_class import EMBEDDER as emb  # noqa: N811
+            except ImportError:   # an older reference tree without the embedder registry: keep the three above
+                emb = None
     if regs is None:
         regs = (MODEL or Registry("MODEL"), DIFFUSION or Registry("DIFFUSION"), AUTO_ENCODER or Registry("AUTO_ENCODER"))
         USING_REFERENCE_REGISTRY = False
