@@ -2,11 +2,15 @@
 
 The reference engine (tools/inferences/inference_videolcm_entrance.py:171-179,233-255) drives
 `diffusers.schedulers.LCMScheduler` (diffusers==0.26.3, tft2v_environment.yaml:60), a third-party dependency
-that is NOT vendored under /root/reference and NOT installed here (no network).  PARITY UNPINNED: this file
-restates the published algorithm (arXiv:2310.04378, multistep consistency sampling; the scheduler's
-documented behaviour) in plain torch; there is no reference run or golden vector behind it.  What the
-tests do pin: the product scheduler (vgen_b200/lcm.py) equals this restatement, the timestep list for the
-engine's arguments is [999, 759, 499, 259], zero terminal SNR holds (alphas_cumprod[999] == 0), and the
+that is NOT vendored under /root/reference and NOT installed here (no network).  PARITY PARTIALLY PINNED: this
+file restates the published algorithm (arXiv:2310.04378, multistep consistency sampling; the scheduler's
+documented behaviour) in plain torch.  Pinned against the reference's in-tree restatements of the scheduler
+(tools/train/train_videolcm_t2v_entrance.py:129-176 -> oracle/make_golden_lcm.py -> tests/golden/lcm_pins.npz):
+boundary_scalings, the x0 expression in sample_loop, the 50-step origin grid; and alphas_cumprod(True) bit-exact
+against the reference's own rescale_zero_terminal_snr (tools/modules/diffusions/schedules.py:143-165).  PARITY
+UNPINNED for the rest (inference timestep selection, re-noising update): no reference run or golden vector
+exists.  What the tests additionally pin: the product scheduler (vgen_b200/lcm.py) equals this restatement, the
+timestep list for the engine's arguments is [999, 759, 499, 259], zero terminal SNR holds (alphas_cumprod[999] == 0), and the
 boundary condition c_skip -> 1, c_out -> 0 at t -> 0.
 
     sample_loop(noise, model, model_kwargs, steps) reproduces the engine loop with CFG off (its default).

@@ -216,6 +216,30 @@ def test_lcm_sampler_parity(golden_dir):
     assert e_mine < 1e-2 and e_mine < 1.25 * e_ref16 + 5e-4
 
 
+def test_lcm_step_against_reference_in_tree_pieces(golden_dir):
+    """LCMScheduler.step on the device against the pieces of diffusers' LCMScheduler the reference restates in-tree
+    (tests/golden/lcm_pins.npz <- tools/train/train_videolcm_t2v_entrance.py:129-150): denoised == c_out * x0 + c_skip * x
+    with the pinned c_skip / c_out / x0, for the four timesteps the engine visits.  Tolerance 1e-3 relative: the product
+    takes the model output in fp16 (the UNet's output dtype), the pins were frozen in fp64."""
+    from vgen_b200.lcm import LCMScheduler
+    g = np.load(os.path.join(golden_dir, "lcm_pins.npz"))
+    shape = g["x0_v"].shape
+    x = synth.tensor("lcm_sample", shape, 1.0, 3)
+    v = synth.tensor("lcm_model_output", shape, 1.0, 4)
+    sched = LCMScheduler(prediction_type="v_prediction", beta_schedule="scaled_linear", clip_sample=False,
+                         timestep_spacing="linspace", rescale_betas_zero_snr=True)
+    sched.set_timesteps(4, device="cuda")
+    assert sched.timesteps.tolist() == g["timesteps"][:4].tolist()
+    for i, t in enumerate(sched.timesteps):
+        xi, vi = x[i:i + 1].cuda(), v[i:i + 1].cuda().half()
+        prev, den = sched.step(vi, t, xi, return_dict=False)
+        want = float(g["c_out"][i]) * torch.from_numpy(g["x0_v"][i:i + 1]) + float(g["c_skip"][i]) * x[i:i + 1].double()
+        err = _rel_l2(den.cpu().double(), want)
+        assert err < 1e-3, (int(t), err)
+        if i == 3:
+            assert torch.equal(prev, den)                # no re-noising after the last step
+
+
 def test_cfg_batching_matches_two_forwards(golden_dir, monkeypatch):
     """diffusion.cfg_forward: one batch-2b forward for the cond / uncond branches == two separate forwards
     (batch entries never interact; only fp32 partial-sum orders inside GroupNorm differ)."""

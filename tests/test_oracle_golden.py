@@ -153,3 +153,40 @@ def test_clip_oracle_matches_reference_golden(golden_dir):
         assert float((x - torch.from_numpy(g[f"{layer}_x"])).abs().max()) < 1e-4 * float(np.abs(g[f"{layer}_x"]).max())
     xi = co.encode_image(sd, image, TINY["vision_cfg"]["head_width"])
     assert float((xi - torch.from_numpy(g["xi"])).abs().max()) < 1e-4 * float(np.abs(g["xi"]).max())
+
+
+def test_lcm_oracle_matches_reference_in_tree_pieces(golden_dir):
+    """Partial pin of the LCM sampler (diffusers absent): boundary scalings, the step-4 x0 formula and the 50-step DDIM
+    grid, frozen from the reference's own in-tree restatements (tools/train/train_videolcm_t2v_entrance.py:129-176,
+    oracle/make_golden_lcm.py) -- oracle and product host math against them."""
+    from oracle import lcm_oracle as lo
+    from vgen_b200.lcm import LCMScheduler
+    g = np.load(os.path.join(golden_dir, "lcm_pins.npz"))
+    ts = g["timesteps"].tolist()
+    s = LCMScheduler(prediction_type="v_prediction", beta_schedule="scaled_linear", clip_sample=False,
+                     timestep_spacing="linspace", rescale_betas_zero_snr=True)
+    for i, t in enumerate(ts):
+        for got in (lo.boundary_scalings(float(t)), s.boundary_scalings(t)):
+            assert got[0] == pytest.approx(float(g["c_skip"][i]), rel=1e-12, abs=0)
+            assert got[1] == pytest.approx(float(g["c_out"][i]), rel=1e-12, abs=0)
+    # x0 (LCMScheduler.step, step 4): the oracle's in-loop expression, v-prediction and epsilon forms
+    abar = lo.alphas_cumprod(True).double()
+    shape = g["x0_v"].shape
+    x = synth.tensor("lcm_sample", shape, 1.0, 3).double()
+    v = synth.tensor("lcm_model_output", shape, 1.0, 4).double()
+    for i, t in enumerate(ts):
+        a = abar[t]
+        x0 = a.sqrt() * x[i] - (1 - a).sqrt() * v[i]                     # lcm_oracle.sample_loop, v-prediction
+        assert np.array_equal(x0.numpy(), g["x0_v"][i])
+        if i:
+            x0e = (x[i] - (1 - a).sqrt() * v[i]) / a.sqrt()
+            assert np.allclose(x0e.numpy(), g["x0_eps"][i - 1], rtol=1e-12, atol=0)
+    # the grid the consistency model was distilled on == the origin grid both schedulers subsample
+    assert g["ddim_grid"].tolist() == sorted(lo.lcm_timesteps(50)) == [20 * k + 19 for k in range(50)]
+    s.set_timesteps(50)
+    assert sorted(s.timesteps.tolist()) == g["ddim_grid"].tolist()
+    assert np.array_equal(g["ddim_abar"], abar.numpy()[g["ddim_grid"]])
+    assert set(lo.lcm_timesteps(4)) <= set(g["ddim_grid"].tolist())
+    # zero-terminal-SNR rescale: the reference's own implementation (schedules.py:143-165) on the same fp32 betas
+    assert np.array_equal(lo.alphas_cumprod(True).numpy(), g["abar_zero_snr"])
+    assert np.array_equal(s.alphas_cumprod.numpy(), g["abar_zero_snr"]) and g["abar_zero_snr"][-1] == 0.0

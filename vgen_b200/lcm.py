@@ -11,7 +11,10 @@
 
 diffusers is a third-party dependency of that engine (diffusers==0.26.3, tft2v_environment.yaml:60) and is
 not installed here, so this file restates the published algorithm of its LCMScheduler (latent consistency
-models, arXiv:2310.04378; multistep consistency sampling): **parity unpinned** -- see DESIGN.md.  Points to
+models, arXiv:2310.04378; multistep consistency sampling): **parity partially pinned** (boundary scalings, x0
+formula and the 50-step grid against tools/train/train_videolcm_t2v_entrance.py:129-176, the zero-SNR rescale against
+tools/modules/diffusions/schedules.py:143-165), timestep selection and re-noising unpinned -- see
+DESIGN.md §4.  Points to
 re-verify against a real diffusers 0.26.3: the timestep list for (50 original steps, 4 inference steps) and
 the treatment of alphas_cumprod[999] == 0 after the zero-terminal-SNR rescale.
 
