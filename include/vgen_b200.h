@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VGEN_B200_ABI_VERSION 1
+#define VGEN_B200_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int vgen_abi_version(void);
@@ -47,6 +47,13 @@ typedef struct vgen_epilogue {
   int64_t residual_ld;
   int geglu;                /* 1: out[rows][n/2] = value * gelu(gate); W rows interleaved per bn block */
   int bn;                   /* N tile (32..256, multiple of 32; GEGLU: multiple of 64); 0 = auto       */
+  /* LayerNorm folded into the GEMM (vgen_linear only): with w = W * diag(gamma) (rounded to fp16), col_sum[n] =
+   * sum_k w[n][k], bias = b + W beta and row_stats[r] = {rstd_r, -mean_r * rstd_r} (vgen_row_stats),
+   *   LN(x) W^T + b  =  rstd_r * (x w^T)[r][n] + (-mean_r rstd_r) * col_sum[n] + bias[n]
+   * so the normalised activations are never written (nn.LayerNorm -> nn.Linear, util.py:694-704,731-741).
+   * Both NULL = off; GEGLU: col_sum is indexed like bias (packed weight rows). */
+  const float* row_stats;   /* fp32 [rows][2] or NULL                                                  */
+  const float* col_sum;     /* fp32 [n] or NULL                                                        */
 } vgen_epilogue;
 
 /* out[m][n] = epi(a[m][:k] . w[n][:k])       -- nn.Linear / 1x1 conv / Conv1d(k=1)
@@ -79,6 +86,11 @@ int vgen_group_norm(const void* x, void* y, int64_t n, int64_t p, int64_t c, con
 /* LayerNorm over the last dim of x[rows][c] (row strides ldx / ldy).  replaces: nn.LayerNorm util.py:694-696,1429 */
 int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx, int64_t ldy, const float* gamma,
                     const float* beta, float eps, void* stream);
+
+/* Statistics of that LayerNorm only: stats[rows][2] = {rstd, -mean * rstd} fp32 (two-pass mean / variance like
+ * vgen_layer_norm; one read of x, 8 bytes written per row) for a GEMM with vgen_epilogue.row_stats.
+ * replaces: the statistics half of nn.LayerNorm util.py:694-696 */
+int vgen_row_stats(const void* x, int64_t rows, int64_t c, int64_t ldx, float eps, float* stats, void* stream);
 
 /* ---- attention ---------------------------------------------------------------------------------- */
 /* softmax(q k^T * scale) v, head_dim 64, no mask (attn_sm100.cu, tcgen05 + TMEM).  q[batch][lq][heads*64]

@@ -148,11 +148,11 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(dll, name), name
     l = lib.load()
-    assert l.vgen_abi_version() == 1 and l.vgen_launch_count() == 0
+    assert l.vgen_abi_version() == 2 and l.vgen_launch_count() == 0
     assert l.vgen_set_tapgemm_impl(7) != 0 and b"impl" in l.vgen_last_error()
     assert l.vgen_set_tapgemm_impl(0) == 0
     assert l.vgen_group_norm_workspace_bytes(2) > 0
-    assert ctypes.sizeof(lib.Epilogue) == 64       # struct vgen_epilogue layout (x86-64 SysV)
+    assert ctypes.sizeof(lib.Epilogue) == 80       # struct vgen_epilogue layout (x86-64 SysV; ABI 2 added row_stats, col_sum)
 
 
 # ------------------------------------------------------------------------------------ multi-process (gloo)
@@ -367,3 +367,34 @@ def test_clip_spec_and_tokenizer(golden_dir):
     _, tok_mod = load_reference_open_clip()
     extra = ["", "naive cafe 42", "a " * 200, "UPPER lower MiXeD", "tab\tand\nnewline", "emoji \U0001F680 \u65e5\u672c\u8a9e"]
     assert torch.equal(ct.tokenize(extra), tok_mod.tokenize(extra))
+
+
+def test_layer_norm_fold_algebra():
+    """ops.fold_layer_norm (host side of vgen_epilogue.row_stats / col_sum): rstd (x w'^T) - mean rstd col_sum + bias' equals
+    LayerNorm -> Linear, including rows whose mean dwarfs their spread (the constant part cancels exactly because col_sum is
+    taken from the ROUNDED weights), and survives the GEGLU row interleave."""
+    import torch
+    from vgen_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    m, k, n = 64, 320, 96
+    x = (torch.randn(m, k, generator=g) * 1.5 + 6.0 * torch.randn(m, 1, generator=g)).half()
+    w, b = torch.randn(n, k, generator=g) * k ** -0.5, torch.randn(n, generator=g)
+    gam, bet = 1.0 + 0.3 * torch.randn(k, generator=g), 0.2 * torch.randn(k, generator=g)
+    ref = torch.nn.functional.layer_norm(x.double(), (k,), gam.double(), bet.double(), 1e-5) @ w.double().t() + b.double()
+    wf, cs, lb = ops.fold_layer_norm(w, b, gam, bet)
+    assert wf.dtype == torch.float16 and cs.dtype == torch.float32 and lb.dtype == torch.float32
+    xd = x.double()
+    mean = xd.mean(1, keepdim=True)
+    rstd = (xd.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    got = rstd * (xd @ wf.double().t()) + (-mean * rstd) * cs.double()[None, :] + lb.double()[None, :]
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-3
+    # a constant row is mapped to bias' exactly
+    const = torch.full((1, k), 3.0, dtype=torch.float64)
+    got_c = (1e-5 ** -0.5) * (const @ wf.double().t()) + (-3.0 * 1e-5 ** -0.5) * cs.double()[None, :] + lb.double()[None, :]
+    assert float((got_c - lb.double()[None, :]).abs().max()) < 1e-2       # 316 * fp32 rounding of col_sum
+    # GEGLU: fold first, then interleave rows; col_sum of the packed rows follows the same permutation as the bias
+    wp, bp = ops.pack_geglu_weight(w * gam[None, :], b + w @ bet, 32)
+    wp16 = wp.half()
+    perm_cs = wp16.double().sum(1)
+    wp_ref, cs_ref = ops.pack_geglu_weight(wf.float(), cs, 32)
+    assert torch.equal(wp_ref.half(), wp16) and torch.allclose(perm_cs.float(), cs_ref, rtol=0, atol=1e-6)

@@ -102,6 +102,56 @@ def group_tapgemm(impl="sm100"):
     geglu_case(256, 320, 1280, 256)
     geglu_case(1000, 640, 2560, 128)
 
+    # nn.LayerNorm folded into the projection (vgen_row_stats + vgen_epilogue.row_stats / col_sum) against LayerNorm -> Linear in
+    # fp32; rows with a large common offset (|mean| = `shift` standard deviations) exercise the cancellation in the fold
+    def ln_case(m, k, n, bias=False, geglu_bn=0, shift=0.0, lda_pad=0):
+        def f():
+            a_full = (rnd(m, k + lda_pad) * (1.0 + torch.rand(m, 1, generator=g).to(dev)) + shift * rnd(m, 1)).half()
+            a = a_full[:, :k]
+            w = rnd(n, k, scale=k ** -0.5)
+            b = rnd(n) if bias else None
+            gam, bet = 1.0 + 0.3 * rnd(k), 0.2 * rnd(k)
+            ref = torch.nn.functional.layer_norm(a.float(), (k,), gam, bet, 1e-5) @ w.t()
+            if b is not None:
+                ref = ref + b
+            if geglu_bn:
+                inner = n // 2
+                proj = ref.half().float()
+                ref = proj[:, :inner] * torch.nn.functional.gelu(proj[:, inner:]).half().float()
+                wb = w * gam[None, :]
+                bb = (b if b is not None else torch.zeros(n, device=dev)) + w @ bet
+                wp, bp = ops.pack_geglu_weight(wb, bb, geglu_bn)
+                wp = wp.half()
+                out = ops.linear(a, wp, bias=bp, geglu=True, bn=geglu_bn, ln=(ops.row_stats(a), wp.double().sum(1).float()))
+            else:
+                wf, cs, lb = ops.fold_layer_norm(w, b, gam, bet)
+                out = ops.linear(a, wf, bias=lb, ln=(ops.row_stats(a), cs))
+            torch.cuda.synchronize()
+            report(f"[{impl}] ln-folded linear m{m} k{k} n{n} bias{int(bias)} geglu{geglu_bn} shift{shift} pad{lda_pad}",
+                   rel_err(out, ref), 2e-3)
+        run_case(f"ln linear m{m} k{k} n{n}", f)
+
+    def stats_case(m, k):
+        def f():
+            a = (rnd(m, k) * 2.0 + 0.5).half()
+            st = ops.row_stats(a)
+            torch.cuda.synchronize()
+            mean = a.float().mean(1)
+            rstd = (a.float().var(1, unbiased=False) + 1e-5).rsqrt()
+            report(f"row_stats m{m} k{k}", rel_err(st, torch.stack([rstd, -mean * rstd], 1)), 2e-5)
+        run_case(f"row_stats m{m} k{k}", f)
+
+    ln_case(1000, 320, 960)
+    ln_case(513, 320, 320, shift=8.0)
+    ln_case(2000, 640, 1920, bias=True, lda_pad=64)
+    ln_case(300, 1280, 1280, shift=3.0)
+    ln_case(1000, 320, 2560, bias=True, geglu_bn=256)
+    ln_case(777, 640, 5120, bias=True, geglu_bn=128, shift=4.0)
+    ln_case(100, 192, 40)                      # scalar epilogue path, LayerNorm width outside the vector kernels' set
+    if impl == "sm100":
+        for (m, k) in [(1000, 320), (1001, 640), (64, 1280), (50, 2560), (33, 100), (7, 4096)]:
+            stats_case(m, k)
+
     def conv_case(nimg, h, w_, c, n, bias=True, gb=False, res=False):
         def f():
             x = rnd(nimg, h, w_, c).half()
@@ -228,25 +278,42 @@ def group_attention():
         o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v))
         return o.permute(0, 2, 1, 3).reshape(b, lq, inner)
 
-    for (b, heads, lq, lk, div, fused) in [(1, 1, 128, 128, 1, False), (1, 1, 256, 128, 1, False), (1, 1, 256, 256, 1, False),
-                                           (2, 2, 300, 300, 1, True), (2, 5, 880, 880, 1, True), (4, 5, 220, 77, 4, False),
-                                           (4, 10, 3520, 145, 2, False), (1, 5, 14080, 14080, 1, True), (3, 1, 96, 96, 1, True),
-                                           (2, 2, 1000, 1, 1, False)]:
-        def f():
-            inner = heads * 64
-            if fused:
-                qkv = rnd(b, lq, 3 * inner, scale=1.0).half()
-                q, k, v = qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:]
-            else:
-                q = rnd(b, lq, inner).half()
-                kv = rnd(b // div, lk, 2 * inner).half()
-                k, v = kv[:, :, :inner], kv[:, :, inner:]
-            out = ops.attention_d64(q, k, v, heads, kv_batch_div=div)
-            torch.cuda.synchronize()
-            kk = k.repeat_interleave(div, dim=0)
-            vv = v.repeat_interleave(div, dim=0)
-            report(f"attention_d64 b{b} h{heads} lq{lq} lk{lk} div{div} fused{int(fused)}", rel_err(out, sdpa(q, kk, vv, heads)), 3e-3)
-        run_case(f"attn {b} {heads} {lq} {lk}", f)
+    # the library's shape heuristic first, then every instantiation of the tcgen05 kernel forced (VGEN_ATTN_TILES: SS form with
+    # 2 q-tiles x 128-key blocks or 3 q-tiles x 64-key blocks -- also without its start-up stagger --, and the TS family with P
+    # in tensor memory, with and without a fraction of the exponentials on the FMA pipe)
+    for (tiles, stagger) in [(None, None), ("2", None), ("3", None), ("3", 0), ("t1", None), ("t1x4", None), ("t2", None), ("t2x8", None)]:
+        for (b, heads, lq, lk, div, fused) in [(1, 1, 128, 128, 1, False), (1, 1, 256, 128, 1, False), (1, 1, 256, 256, 1, False),
+                                               (2, 2, 300, 300, 1, True), (2, 5, 880, 880, 1, True), (4, 5, 220, 77, 4, False),
+                                               (4, 10, 3520, 145, 2, False), (1, 5, 14080, 14080, 1, True), (3, 1, 96, 96, 1, True),
+                                               (2, 2, 1000, 1, 1, False), (1, 2, 385, 64, 1, False), (1, 2, 400, 600, 1, False),
+                                               (2, 1, 384, 65, 2, False)]:
+            if stagger == 0 and lq > 1000:
+                continue
+
+            def f():
+                inner = heads * 64
+                if fused:
+                    qkv = rnd(b, lq, 3 * inner, scale=1.0).half()
+                    q, k, v = qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:]
+                else:
+                    q = rnd(b, lq, inner).half()
+                    kv = rnd(b // div, lk, 2 * inner).half()
+                    k, v = kv[:, :, :inner], kv[:, :, inner:]
+                if tiles is not None:      # None: the library's shape heuristic
+                    os.environ["VGEN_ATTN_TILES"] = tiles
+                if stagger is not None:
+                    os.environ["VGEN_ATTN_STAGGER"] = str(stagger)
+                try:
+                    out = ops.attention_d64(q, k, v, heads, kv_batch_div=div)
+                    torch.cuda.synchronize()
+                finally:
+                    os.environ.pop("VGEN_ATTN_TILES", None)
+                    os.environ.pop("VGEN_ATTN_STAGGER", None)
+                kk = k.repeat_interleave(div, dim=0)
+                vv = v.repeat_interleave(div, dim=0)
+                report(f"attention_d64 tiles{tiles} stagger{stagger} b{b} h{heads} lq{lq} lk{lk} div{div} fused{int(fused)}",
+                       rel_err(out, sdpa(q, kk, vv, heads)), 3e-3)
+            run_case(f"attn x{tiles} {b} {heads} {lq} {lk}", f)
 
     # head_dim 512 single-head flash attention (VAE AttnBlock): ragged lengths, fused qkv views, the 1280x704 size,
     # large-magnitude inputs (scores ~ +-60: fp32 statistics must hold where fp16 logits would not), batches of 3 videos

@@ -72,6 +72,11 @@ static int fill_epilogue(TapGemmArgs* t, void* out, long ldo, const vgen_epilogu
   e.residual = epi ? reinterpret_cast<const __half*>(epi->residual) : nullptr;
   e.ldr = epi ? epi->residual_ld : 0;
   e.geglu = epi ? epi->geglu : 0;
+  e.row_stats = epi ? reinterpret_cast<const float2*>(epi->row_stats) : nullptr;
+  e.col_sum = epi ? epi->col_sum : nullptr;
+  VG_REQUIRE((e.row_stats == nullptr) == (e.col_sum == nullptr), "tapgemm: row_stats and col_sum go together");
+  VG_REQUIRE((reinterpret_cast<uintptr_t>(e.row_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(e.col_sum) & 15) == 0,
+             "tapgemm: row_stats must be 8-byte and col_sum 16-byte aligned");
   return 0;
 }
 
@@ -135,7 +140,10 @@ int vgen_linear(const void* a, int64_t m, int64_t k, int64_t lda, const void* w,
   s.num_taps = 1;
   s.tap1[0] = s.tap2[0] = s.tap3[0] = 0;
   s.n = (int)n;
-  fill_epilogue(&t, out, ldo, epi);
+  {
+    int rc = fill_epilogue(&t, out, ldo, epi);
+    if (rc) return rc;
+  }
   VG_REQUIRE(!t.epi.group_bias, "vgen_linear: group_bias is only defined for conv entries");
   return finish_and_launch(&t, epi, stream);
 }
@@ -165,7 +173,11 @@ int vgen_conv2d_3x3(const void* x, int64_t nimg, int64_t h, int64_t w_, int64_t 
       s.tap3[ky * 3 + kx] = 0;
     }
   s.n = (int)n;
-  fill_epilogue(&t, out, ldo, epi);
+  {
+    int rc = fill_epilogue(&t, out, ldo, epi);
+    if (rc) return rc;
+  }
+  VG_REQUIRE(!t.epi.row_stats, "vgen_conv2d_3x3: row_stats (folded LayerNorm) is only defined for vgen_linear");
   return finish_and_launch(&t, epi, stream);
 }
 
@@ -198,8 +210,12 @@ int vgen_tconv3_batch(const void* x, int64_t batch, int64_t f, int64_t hw, int64
     s.tap3[kt] = 0;
   }
   s.n = (int)n;
-  fill_epilogue(&t, out, ldo, epi);
+  {
+    int rc = fill_epilogue(&t, out, ldo, epi);
+    if (rc) return rc;
+  }
   VG_REQUIRE(!t.epi.group_bias, "vgen_tconv3: group_bias not supported");
+  VG_REQUIRE(!t.epi.row_stats, "vgen_tconv3: row_stats (folded LayerNorm) is only defined for vgen_linear");
   return finish_and_launch(&t, epi, stream);
 }
 

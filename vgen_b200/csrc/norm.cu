@@ -263,10 +263,13 @@ static int gn_geometry(long N, long P, int C, GnGeom* g) {
 // One warp per row, the row lives in registers (C <= 2560), two-pass mean / variance like ATen.  Warps
 // walk rows with a grid stride and prefetch the next row's raw vectors before reducing the current one,
 // so every warp always has loads in flight.
-template <int MAXV>
+// kStats: nothing is written but the row's statistics {rstd, -mean * rstd} (vgen_row_stats: the LayerNorm itself is folded
+// into the GEMM that consumes the row, see vgen_epilogue.row_stats).
+template <int MAXV, bool kStats>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        long rows, int C, long ldx, long ldy, float eps) {
+                                                        long rows, int C, long ldx, long ldy, float eps,
+                                                        float2* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int C8 = C >> 3;
   const long warps_total = (long)gridDim.x * (blockDim.x >> 5);
@@ -319,6 +322,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     }
     q = warp_sum(q);
     const float rstd = rsqrtf(q / (float)C + eps);
+    if (kStats) {
+      if (lane == 0) stats[row] = make_float2(rstd, -mean * rstd);
+      continue;
+    }
     __half* yr = y + row * ldy;
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
@@ -355,10 +362,11 @@ __device__ __forceinline__ float4 ldg_f4_pinned(const float* p) {
 // Rows narrower than a warp's worth of 16-byte vectors (C = 320 / 640: 40 / 80 vectors): LPR lanes share a row and a
 // warp normalises 32/LPR rows at once, so every load instruction is fully populated and each lane keeps VPL (= 5)
 // 16-byte loads in flight (the warp-per-row kernel had 1.25 per lane at C = 320 and ran at 3.9 TB/s).
-template <int LPR, int VPL>
+template <int LPR, int VPL, bool kStats>
 __global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                long rows, int C, long ldx, long ldy, float eps) {
+                                                                long rows, int C, long ldx, long ldy, float eps,
+                                                                float2* __restrict__ stats) {
   constexpr int RW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, li = lane % LPR;
@@ -412,6 +420,10 @@ __global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)C + eps);
+    if (kStats) {
+      if (live && li == 0) stats[row] = make_float2(rstd, -mean * rstd);
+      continue;
+    }
     if (live) {
       __half* yr = y + row * ldy;
 #pragma unroll
@@ -443,9 +455,10 @@ __global__ void __launch_bounds__(256) layernorm_grouped_kernel(const __half* __
 }
 
 // generic small-C LayerNorm (any C, scalar): one thread per row
+template <bool kStats>
 __global__ void layernorm_small_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, long rows, int C,
-                                       long ldx, long ldy, float eps) {
+                                       long ldx, long ldy, float eps, float2* __restrict__ stats) {
   const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const __half* xr = x + row * ldx;
@@ -458,7 +471,56 @@ __global__ void layernorm_small_kernel(const __half* __restrict__ x, __half* __r
     q += d * d;
   }
   const float rstd = rsqrtf(q / C + eps);
-  for (int c = 0; c < C; ++c) y[row * ldy + c] = __float2half_rn((__half2float(xr[c]) - mean) * rstd * gamma[c] + beta[c]);
+  if (kStats) {
+    stats[row] = make_float2(rstd, -mean * rstd);
+  } else {
+    for (int c = 0; c < C; ++c) y[row * ldy + c] = __float2half_rn((__half2float(xr[c]) - mean) * rstd * gamma[c] + beta[c]);
+  }
+}
+
+// vgen_layer_norm (kStats = false) and vgen_row_stats (kStats = true) share the kernel choice.
+template <bool kStats>
+static int layer_norm_launch(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx, int64_t ldy, const float* gamma,
+                             const float* beta, float eps, float2* stats, void* stream) {
+  if (rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __half* xp = reinterpret_cast<const __half*>(x);
+  __half* yp = reinterpret_cast<__half*>(y);
+  const bool vec = (c % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && c <= 2560 &&
+                   ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
+  if (vec) {
+    const int wpb = 8;
+    long blocks = (rows + wpb - 1) / wpb;
+    const long cap = 16L * sm_count();  // grid-stride: ~16 resident blocks' worth per SM
+    if (blocks > cap) blocks = cap;
+    const int c8 = (int)c / 8;
+    if (c8 == 40 || c8 == 80) {
+      const int rw = c8 == 40 ? 4 : 2;  // rows per warp
+      long gblocks = ((rows + rw - 1) / rw + wpb - 1) / wpb;
+      if (gblocks > cap) gblocks = cap;
+      if (c8 == 40)
+        launch_kernel(layernorm_grouped_kernel<8, 5, kStats>, dim3((unsigned)gblocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps, stats);
+      else
+        launch_kernel(layernorm_grouped_kernel<16, 5, kStats>, dim3((unsigned)gblocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps, stats);
+      VG_LAUNCH_CHECK("layernorm_grouped_kernel");
+      return 0;
+    }
+    if (c8 <= 32)
+      launch_kernel(layernorm_kernel<1, kStats>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps, stats);
+    else if (c8 <= 64)
+      launch_kernel(layernorm_kernel<2, kStats>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps, stats);
+    else if (c8 <= 160)
+      launch_kernel(layernorm_kernel<5, kStats>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps, stats);
+    else
+      launch_kernel(layernorm_kernel<10, kStats>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps, stats);
+    VG_LAUNCH_CHECK("layernorm_kernel");
+  } else {
+    const unsigned blocks = (unsigned)((rows + 127) / 128);
+    launch_kernel(layernorm_small_kernel<kStats>, dim3(blocks), dim3(128), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps, stats);
+    VG_LAUNCH_CHECK("layernorm_small_kernel");
+  }
+  return 0;
 }
 
 }  // namespace vg
@@ -517,45 +579,14 @@ int vgen_layer_norm(const void* x, void* y, int64_t rows, int64_t c, int64_t ldx
                     const float* beta, float eps, void* stream) {
   VG_REQUIRE(x && y && gamma && beta, "vgen_layer_norm: null pointer");
   VG_REQUIRE(rows >= 0 && c > 0 && ldx >= c && ldy >= c, "vgen_layer_norm: bad shape");
-  if (rows == 0) return 0;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const __half* xp = reinterpret_cast<const __half*>(x);
-  __half* yp = reinterpret_cast<__half*>(y);
-  const bool vec = (c % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && c <= 2560 &&
-                   ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
-  if (vec) {
-    const int wpb = 8;
-    long blocks = (rows + wpb - 1) / wpb;
-    const long cap = 16L * sm_count();  // grid-stride: ~16 resident blocks' worth per SM
-    if (blocks > cap) blocks = cap;
-    const int c8 = (int)c / 8;
-    if (c8 == 40 || c8 == 80) {
-      const int rw = c8 == 40 ? 4 : 2;  // rows per warp
-      long gblocks = ((rows + rw - 1) / rw + wpb - 1) / wpb;
-      if (gblocks > cap) gblocks = cap;
-      if (c8 == 40)
-        launch_kernel(layernorm_grouped_kernel<8, 5>, dim3((unsigned)gblocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
-      else
-        launch_kernel(layernorm_grouped_kernel<16, 5>, dim3((unsigned)gblocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
-      VG_LAUNCH_CHECK("layernorm_grouped_kernel");
-      return 0;
-    }
-    if (c8 <= 32)
-      launch_kernel(layernorm_kernel<1>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
-    else if (c8 <= 64)
-      launch_kernel(layernorm_kernel<2>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
-    else if (c8 <= 160)
-      launch_kernel(layernorm_kernel<5>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
-    else
-      launch_kernel(layernorm_kernel<10>, dim3((unsigned)blocks), dim3(32 * wpb), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
-    VG_LAUNCH_CHECK("layernorm_kernel");
-  } else {
-    const unsigned blocks = (unsigned)((rows + 127) / 128);
-    launch_kernel(layernorm_small_kernel, dim3(blocks), dim3(128), 0, st, xp, yp, gamma, beta, rows, (int)c, ldx, ldy, eps);
-    VG_LAUNCH_CHECK("layernorm_small_kernel");
-  }
-  return 0;
+  return layer_norm_launch<false>(x, y, rows, c, ldx, ldy, gamma, beta, eps, nullptr, stream);
+}
+
+int vgen_row_stats(const void* x, int64_t rows, int64_t c, int64_t ldx, float eps, float* stats, void* stream) {
+  VG_REQUIRE(x && stats, "vgen_row_stats: null pointer");
+  VG_REQUIRE(rows >= 0 && c > 0 && ldx >= c, "vgen_row_stats: bad shape");
+  VG_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 7) == 0, "vgen_row_stats: stats must be 8-byte aligned");
+  return layer_norm_launch<true>(x, nullptr, rows, c, ldx, c, nullptr, nullptr, eps, reinterpret_cast<float2*>(stats), stream);
 }
 
 }  // extern "C"

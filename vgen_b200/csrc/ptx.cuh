@@ -200,6 +200,17 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on the 128 lanes, K-major, 16-bit elements packed two per
+// 32-bit column: element (m, k) = lane m, column k / 2, half k % 2) is read from tensor memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -231,6 +242,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+// Compiler-level pin: the 32 registers are (re)defined HERE, i.e. after whatever volatile asm precedes this call (a
+// tcgen05.wait::ld issued long after the tcgen05.ld that names them) -- no instruction is emitted.
+__device__ __forceinline__ void reg_pin32(uint32_t (&v)[32]) {
+  asm volatile(""
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> TMEM (same 32x32b shape as tmem_ld32)
@@ -342,6 +364,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// three-input maximum (FMNMX3) and packed two-lane fp32 FMA (FFMA2) of sm_100: half the issue slots of their scalar forms
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// {a.x * s.x + m.x, a.y * s.y + m.y}, each lane rounded like fmaf
+__device__ __forceinline__ float2 fma2(float ax, float ay, float2 s, float2 m) {
+  unsigned long long ra, rs, rm, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rs) : "f"(s.x), "f"(s.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rm) : "f"(m.x), "f"(m.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rs), "l"(rm));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -71,6 +71,8 @@ struct TapGemmEpilogue {
   const __half* residual;    // [rows][n] or null: added after rounding
   long ldr;
   int geglu;                 // out has n/2 columns: value * gelu(gate)
+  const float2* row_stats;   // [rows] {rstd, -mean * rstd} or null: LayerNorm folded into the epilogue (linear only)
+  const float* col_sum;      // [n]: sum_k w[n][k]   (GEGLU: indexed like bias)
 };
 
 struct TapGemmArgs {

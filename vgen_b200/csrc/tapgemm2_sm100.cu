@@ -37,10 +37,13 @@ struct alignas(64) TapGemm2Params {
   int total_pair_tiles;  // ceil(m_tiles / 2) * nb
 };
 
-template <bool kGeglu>
+// kEpi: bit 0 = GEGLU epilogue, bit 1 = LayerNorm folded into the epilogue (TapGemmEpilogue.row_stats); separate
+// instantiations because the epilogues have very different register needs.
+template <int kEpi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     tapgemm_sm100_2cta_kernel(const __grid_constant__ TapGemm2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr bool kGeglu = (kEpi & 1) != 0, kLn = (kEpi & 2) != 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
@@ -215,7 +218,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
       mbar_wait(&tfull_bar[as], aph, 34);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile<kGeglu>(s, e, t, est, vec_ok, out_n, cg, 2);
+      tapgemm_epilogue_tile<kGeglu, kLn>(s, e, t, est, vec_ok, out_n, cg, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
@@ -298,15 +301,22 @@ int tapgemm_sm100_2cta_launch(const TapGemmArgs& a, cudaStream_t stream) {
 
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_2cta_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.mark();
   }
   int clusters = sm_count() / 2;
   if (clusters > p.total_pair_tiles) clusters = p.total_pair_tiles;
   if (clusters < 1) return 0;
-  if (a.epi.geglu) launch_kernel(tapgemm_sm100_2cta_kernel<true>, dim3(2 * clusters), dim3(kThreads2), smem, stream, p);
-  else launch_kernel(tapgemm_sm100_2cta_kernel<false>, dim3(2 * clusters), dim3(kThreads2), smem, stream, p);
+  const int kind = (a.epi.geglu ? 1 : 0) | (a.epi.row_stats ? 2 : 0);
+  if (a.epi.row_stats) VG_REQUIRE(!a.epi.residual && !a.epi.group_bias && s.num_taps == 1 && s.d2 == 1 && s.d3 == 1,
+                                  "tapgemm: a folded LayerNorm goes with a plain linear (no residual / per-frame bias)");
+  if (kind == 3) launch_kernel(tapgemm_sm100_2cta_kernel<3>, dim3(2 * clusters), dim3(kThreads2), smem, stream, p);
+  else if (kind == 2) launch_kernel(tapgemm_sm100_2cta_kernel<2>, dim3(2 * clusters), dim3(kThreads2), smem, stream, p);
+  else if (kind == 1) launch_kernel(tapgemm_sm100_2cta_kernel<1>, dim3(2 * clusters), dim3(kThreads2), smem, stream, p);
+  else launch_kernel(tapgemm_sm100_2cta_kernel<0>, dim3(2 * clusters), dim3(kThreads2), smem, stream, p);
   VG_LAUNCH_CHECK("tapgemm_sm100_2cta_kernel");
   return 0;
 }

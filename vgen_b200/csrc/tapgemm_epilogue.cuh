@@ -136,7 +136,9 @@ __device__ __forceinline__ void epi_stage_drain(const EpiStore& st) {
 // a TMEM lane quadrant and split the columns between them).
 // kGeglu is a template parameter of the kernels: the two epilogues have very different register needs, and
 // compiled into one kernel each paid for the other's allocation and schedule.
-template <bool kGeglu>
+// kLn: LayerNorm folded into the GEMM (TapGemmEpilogue.row_stats / col_sum): the accumulator row is scaled by the row's rstd and
+// shifted by (-mean * rstd) * col_sum[n]; such launches carry no residual / per-frame bias, whose registers the column sums use.
+template <bool kGeglu, bool kLn>
 __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, const TapGemmEpilogue& e, const EpiRow& t,
                                                       EpiStore& st, bool vec_ok, int out_n, int chunk0, int chunk_step) {
   const int BN = s.bn;
@@ -145,6 +147,12 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
     __half* orow = e.out + t.row * e.ldo;
     const __half* rrow = e.residual ? e.residual + t.row * e.ldr : nullptr;
     const __half* grow = e.group_bias ? e.group_bias + (long)fd_div(e.f_group_bias_div, t.i3) * e.ld_group_bias : nullptr;
+    float ln_scale = e.alpha, ln_shift = 0.f;   // kLn: rstd (* alpha) and -mean * rstd of this thread's row
+    if (kLn && t.row_ok) {
+      const float2 rs = __ldg(e.row_stats + t.row);
+      ln_scale = rs.x * e.alpha;
+      ln_shift = rs.y * e.alpha;
+    }
     for (int c0 = chunk0 * 32; c0 < BN; c0 += chunk_step * 32) {
       const int nbase = n0 + c0;
       if (nbase >= s.n) break;  // uniform over the column group
@@ -154,7 +162,7 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
       const bool fast = vec_ok && t.row_ok && full;
       // issue the (HBM / L2 latency) residual and per-frame-bias loads before blocking on the TMEM load
       uint4 r4[4], g4[4];
-      float4 b4[8];
+      float4 b4[8], c4[8];
       const bool staged = st.tma && vec_ok && full;  // uniform over the column group
       const bool res_tile = st.res_tma && staged;    // this chunk's residual was requested by TMA
       if (res_tile) {
@@ -165,8 +173,12 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
       if (fast) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-          if (rrow && !res_tile) r4[j8] = __ldg(reinterpret_cast<const uint4*>(rrow + nbase + j8 * 8));
-          if (grow) g4[j8] = __ldg(reinterpret_cast<const uint4*>(grow + nbase + j8 * 8));
+          if (!kLn && rrow && !res_tile) r4[j8] = __ldg(reinterpret_cast<const uint4*>(rrow + nbase + j8 * 8));
+          if (!kLn && grow) g4[j8] = __ldg(reinterpret_cast<const uint4*>(grow + nbase + j8 * 8));
+          if (kLn) {  // col_sum is 16-byte aligned (checked by the launcher), nbase a multiple of 32
+            c4[2 * j8] = __ldg(reinterpret_cast<const float4*>(e.col_sum + nbase + j8 * 8));
+            c4[2 * j8 + 1] = __ldg(reinterpret_cast<const float4*>(e.col_sum + nbase + j8 * 8 + 4));
+          }
           if (e.bias) {  // vec_ok implies n % 8 == 0; bias tensors are 16-byte aligned
             b4[2 * j8] = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8));
             b4[2 * j8 + 1] = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + j8 * 8 + 4));
@@ -188,19 +200,26 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
         for (int j8 = 0; j8 < 4; ++j8) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * e.alpha;
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * ln_scale;
           if (e.bias) {
             const float4 b0 = b4[2 * j8], b1 = b4[2 * j8 + 1];
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
-          if (grow) {
+          if (kLn) {
+            const float4 c0v = c4[2 * j8], c1v = c4[2 * j8 + 1];
+            f[0] = fmaf(ln_shift, c0v.x, f[0]); f[1] = fmaf(ln_shift, c0v.y, f[1]);
+            f[2] = fmaf(ln_shift, c0v.z, f[2]); f[3] = fmaf(ln_shift, c0v.w, f[3]);
+            f[4] = fmaf(ln_shift, c1v.x, f[4]); f[5] = fmaf(ln_shift, c1v.y, f[5]);
+            f[6] = fmaf(ln_shift, c1v.z, f[6]); f[7] = fmaf(ln_shift, c1v.w, f[7]);
+          }
+          if (!kLn && grow) {
             // reference: h (fp16 conv output) + emb_out (fp16) -> fp16  (util.py:909-919)
             const __half* gh = reinterpret_cast<const __half*>(&g4[j8]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __half2float(__float2half_rn(f[j])) + __half2float(gh[j]);
           }
-          if (rrow) {
+          if (!kLn && rrow) {
             const __half* rh = reinterpret_cast<const __half*>(&r4[j8]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __half2float(__float2half_rn(f[j])) + __half2float(rh[j]);
@@ -217,8 +236,9 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
         for (int j = 0; j < 32; ++j) {
           const int n = nbase + j;
           if (n >= s.n) break;
-          float a = __uint_as_float(v[j]) * e.alpha;
+          float a = __uint_as_float(v[j]) * ln_scale;
           if (e.bias) a += e.bias[n];
+          if (kLn) a = fmaf(ln_shift, e.col_sum[n], a);
           if (grow) a = __half2float(__float2half_rn(a)) + __half2float(grow[n]);
           if (rrow) a = __half2float(__float2half_rn(a)) + __half2float(rrow[n]);
           orow[n] = __float2half_rn(a);
@@ -232,6 +252,12 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
     const int hb = BN >> 1;
     const int o0 = t.nb_i * hb;
     __half* orow = e.out + t.row * e.ldo;
+    float ln_scale = e.alpha, ln_shift = 0.f;
+    if (kLn && t.row_ok) {
+      const float2 rs = __ldg(e.row_stats + t.row);
+      ln_scale = rs.x * e.alpha;
+      ln_shift = rs.y * e.alpha;
+    }
     for (int c0 = chunk0 * 32; c0 < hb; c0 += chunk_step * 32) {
       const int obase = o0 + c0;
       if (obase >= out_n) break;  // uniform over the column group
@@ -255,14 +281,22 @@ __device__ __forceinline__ void tapgemm_epilogue_tile(const TapGemmShape& s, con
             bv = __ldg(reinterpret_cast<const float4*>(e.bias + wbase + j4 * 4));
             bg = __ldg(reinterpret_cast<const float4*>(e.bias + wbase + hb + j4 * 4));
           }
+          if (kLn) {  // shift = bias + (-mean rstd) * col_sum, per packed weight row
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(e.col_sum + wbase + j4 * 4));
+            const float4 cg = __ldg(reinterpret_cast<const float4*>(e.col_sum + wbase + hb + j4 * 4));
+            bv.x = fmaf(ln_shift, cv.x, bv.x); bv.y = fmaf(ln_shift, cv.y, bv.y);
+            bv.z = fmaf(ln_shift, cv.z, bv.z); bv.w = fmaf(ln_shift, cv.w, bv.w);
+            bg.x = fmaf(ln_shift, cg.x, bg.x); bg.y = fmaf(ln_shift, cg.y, bg.y);
+            bg.z = fmaf(ln_shift, cg.z, bg.z); bg.w = fmaf(ln_shift, cg.w, bg.w);
+          }
           const float bva[4] = {bv.x, bv.y, bv.z, bv.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
 #pragma unroll
           for (int jj = 0; jj < 4; jj += 2) {
             const int j = j4 * 4 + jj;
-            const __half2 a2 = __floats2half2_rn(fmaf(__uint_as_float(v[j]), e.alpha, bva[jj]),
-                                                 fmaf(__uint_as_float(v[j + 1]), e.alpha, bva[jj + 1]));
-            const float2 b2 = __half22float2(__floats2half2_rn(fmaf(__uint_as_float(g[j]), e.alpha, bga[jj]),
-                                                               fmaf(__uint_as_float(g[j + 1]), e.alpha, bga[jj + 1])));
+            const __half2 a2 = __floats2half2_rn(fmaf(__uint_as_float(v[j]), ln_scale, bva[jj]),
+                                                 fmaf(__uint_as_float(v[j + 1]), ln_scale, bva[jj + 1]));
+            const float2 b2 = __half22float2(__floats2half2_rn(fmaf(__uint_as_float(g[j]), ln_scale, bga[jj]),
+                                                               fmaf(__uint_as_float(g[j + 1]), ln_scale, bga[jj + 1])));
             const __half2 o2 = __hmul2(a2, __floats2half2_rn(gelu_erf(b2.x), gelu_erf(b2.y)));
             o[j >> 1] = *reinterpret_cast<const uint32_t*>(&o2);
           }

@@ -35,20 +35,28 @@ __global__ void tapgemm_simt_kernel(const __half* __restrict__ A, long st1, long
     return acc;
   };
 
+  // folded LayerNorm (linear only: row = i1): acc * rstd + (-mean rstd) * col_sum
+  const float ln_scale = e.row_stats ? e.row_stats[row].x * e.alpha : e.alpha;
+  const float ln_shift = e.row_stats ? e.row_stats[row].y * e.alpha : 0.f;
   float a;
   if (!e.geglu) {
-    a = dot(n) * e.alpha;
+    a = dot(n) * ln_scale;
     if (e.bias) a += e.bias[n];
+    if (e.row_stats) a = fmaf(ln_shift, e.col_sum[n], a);
     if (e.group_bias) a = __half2float(__float2half_rn(a)) + __half2float(e.group_bias[(long)(i3 / e.group_bias_div) * e.ld_group_bias + n]);
     if (e.residual) a = __half2float(__float2half_rn(a)) + __half2float(e.residual[row * e.ldr + n]);
   } else {
     const int hb = s.bn / 2;
     const int blk = n / hb, j = n % hb;
     const int wv = blk * s.bn + j, wg = wv + hb;
-    float v = dot(wv) * e.alpha, g = dot(wg) * e.alpha;
+    float v = dot(wv) * ln_scale, g = dot(wg) * ln_scale;
     if (e.bias) {
       v += e.bias[wv];
       g += e.bias[wg];
+    }
+    if (e.row_stats) {
+      v = fmaf(ln_shift, e.col_sum[wv], v);
+      g = fmaf(ln_shift, e.col_sum[wg], g);
     }
     const float v16 = __half2float(__float2half_rn(v));
     const float g16 = __half2float(__float2half_rn(g));

@@ -48,10 +48,13 @@ struct alignas(64) TapGemmKernelParams {
   int b_slot_bytes;  // smem bytes reserved per stage for the W tile (>= BN*128, multiple of 1024)
 };
 
-template <bool kGeglu>
+// kEpi: bit 0 = GEGLU epilogue, bit 1 = LayerNorm folded into the epilogue (TapGemmEpilogue.row_stats); separate
+// instantiations because the epilogues have very different register needs.
+template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid_constant__ TapGemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment is required by the 128B swizzle atom (8 rows x 128 B).
+  constexpr bool kGeglu = (kEpi & 1) != 0, kLn = (kEpi & 2) != 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_sm100_kernel(const __grid
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       t.t_row = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-      tapgemm_epilogue_tile<kGeglu>(s, e, t, est, vec_ok, out_n, cg, 2);
+      tapgemm_epilogue_tile<kGeglu, kLn>(s, e, t, est, vec_ok, out_n, cg, 2);
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -303,15 +306,22 @@ int tapgemm_sm100_launch(const TapGemmArgs& a, cudaStream_t stream) {
 
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(tapgemm_sm100_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_once.mark();
   }
   int grid = sm_count();
   if (grid > s.total_tiles) grid = s.total_tiles;
   if (grid < 1) return 0;
-  if (a.epi.geglu) launch_kernel(tapgemm_sm100_kernel<true>, dim3(grid), dim3(kThreads), smem, stream, p);
-  else launch_kernel(tapgemm_sm100_kernel<false>, dim3(grid), dim3(kThreads), smem, stream, p);
+  const int kind = (a.epi.geglu ? 1 : 0) | (a.epi.row_stats ? 2 : 0);
+  if (a.epi.row_stats) VG_REQUIRE(!a.epi.residual && !a.epi.group_bias && s.num_taps == 1 && s.d2 == 1 && s.d3 == 1,
+                                  "tapgemm: a folded LayerNorm goes with a plain linear (no residual / per-frame bias)");
+  if (kind == 3) launch_kernel(tapgemm_sm100_kernel<3>, dim3(grid), dim3(kThreads), smem, stream, p);
+  else if (kind == 2) launch_kernel(tapgemm_sm100_kernel<2>, dim3(grid), dim3(kThreads), smem, stream, p);
+  else if (kind == 1) launch_kernel(tapgemm_sm100_kernel<1>, dim3(grid), dim3(kThreads), smem, stream, p);
+  else launch_kernel(tapgemm_sm100_kernel<0>, dim3(grid), dim3(kThreads), smem, stream, p);
   VG_LAUNCH_CHECK("tapgemm_sm100_kernel");
   return 0;
 }

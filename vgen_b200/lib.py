@@ -29,6 +29,8 @@ class Epilogue(ctypes.Structure):
         ("residual_ld", ctypes.c_int64),
         ("geglu", ctypes.c_int),
         ("bn", ctypes.c_int),
+        ("row_stats", ctypes.c_void_p),
+        ("col_sum", ctypes.c_void_p),
     ]
 
 
@@ -50,6 +52,7 @@ _SIGNATURES = {
     "vgen_group_norm_workspace_bytes": [_i64],
     "vgen_group_norm": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _f32, _i32, _vp, _vp],
     "vgen_layer_norm": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _f32, _vp],
+    "vgen_row_stats": [_vp, _i64, _i64, _i64, _f32, _vp, _vp],
     "vgen_attention_d64": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "vgen_attention_d512": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
     "vgen_attention_d64_debug": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _vp],
@@ -100,8 +103,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, ctypes.c_int)
-    if lib.vgen_abi_version() != 1:
-        raise VgenError(f"ABI version mismatch: library {lib.vgen_abi_version()} != binding 1")
+    if lib.vgen_abi_version() != 2:
+        raise VgenError(f"ABI version mismatch: library {lib.vgen_abi_version()} != binding 2")
     _lib = lib
     return lib
 

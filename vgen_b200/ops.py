@@ -84,10 +84,19 @@ def _rows_view(t, name):
     return t2, t2.stride(0)
 
 
-def _epilogue(n_out, bias=None, group_bias=None, residual=None, alpha=1.0, geglu=False, bn=0, group_div=1):
+def _epilogue(n_out, bias=None, group_bias=None, residual=None, alpha=1.0, geglu=False, bn=0, group_div=1, ln=None):
     e = Epilogue()
     e.alpha = float(alpha)
     keep = []
+    if ln is not None:   # (row_stats [rows, 2] fp32, col_sum [n] fp32): LayerNorm folded into the GEMM
+        stats, col_sum = ln
+        if stats.dtype != torch.float32 or col_sum.dtype != torch.float32 or not stats.is_contiguous() or not col_sum.is_contiguous():
+            raise _l.VgenError("ln: row_stats and col_sum must be contiguous fp32 tensors")
+        if residual is not None or group_bias is not None:
+            raise _l.VgenError("ln: a folded LayerNorm cannot be combined with residual / group_bias")
+        e.row_stats = stats.data_ptr()
+        e.col_sum = col_sum.data_ptr()
+        keep += [stats, col_sum]
     if bias is not None:
         if bias.dtype != torch.float32:
             raise _l.VgenError("bias must be fp32")
@@ -112,8 +121,11 @@ def _epilogue(n_out, bias=None, group_bias=None, residual=None, alpha=1.0, geglu
     return e, keep
 
 
-def linear(a, w, bias=None, residual=None, alpha=1.0, geglu=False, out=None, bn=0):
-    """out[m, n] = epi(a[m, k] @ w[n, k]^T).  `a` may be a row-strided 2-D view."""
+def linear(a, w, bias=None, residual=None, alpha=1.0, geglu=False, out=None, bn=0, ln=None):
+    """out[m, n] = epi(a[m, k] @ w[n, k]^T).  `a` may be a row-strided 2-D view.
+
+    ln = (row_stats(a), col_sum): `a` is the INPUT of a LayerNorm whose affine part was folded into w / bias
+    (fold_layer_norm); the epilogue applies the per-row statistics, so LN(a) is never materialised."""
     _chk16(a, "a"), _chk16(w, "w")
     lead = a.shape[:-1]
     a2, lda = _rows_view(a, "a")
@@ -125,10 +137,12 @@ def linear(a, w, bias=None, residual=None, alpha=1.0, geglu=False, out=None, bn=
     if out is None:
         out = torch.empty(*lead, n_out, device=a.device, dtype=torch.float16)
     o2, ldo = _rows_view(out, "out")
-    e, keep = _epilogue(n_out, bias, None, residual, alpha, geglu, bn)
+    if ln is not None and (ln[0].shape != (m, 2) or ln[1].numel() != n):
+        raise _l.VgenError(f"linear: ln shapes {tuple(ln[0].shape)} / {tuple(ln[1].shape)} do not match m={m}, n={n}")
+    e, keep = _epilogue(n_out, bias, None, residual, alpha, geglu, bn, ln=ln)
     rc = _run("tapgemm", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n_out),
               lambda: _l.load().vgen_linear(_p(a2), m, k, lda, _p(w), n, _p(o2), ldo, ctypes.byref(e), _stream()),
-              tag=f"linear m{m} k{k} n{n}{' geglu' if geglu else ''}{' res' if residual is not None else ''}")
+              tag=f"linear m{m} k{k} n{n}{' geglu' if geglu else ''}{' res' if residual is not None else ''}{' ln' if ln is not None else ''}")
     _l.check(rc, "vgen_linear")
     return out
 
@@ -249,6 +263,31 @@ def layer_norm(x, gamma, beta, eps=1e-5, out=None):
               tag=f"rows{rows} c{c}")
     _l.check(rc, "vgen_layer_norm")
     return out
+
+
+def row_stats(x, eps=1e-5):
+    """LayerNorm statistics of the rows of x [rows, c] -> fp32 [rows, 2] = {rstd, -mean * rstd} (for linear(..., ln=...))."""
+    _chk16(x, "x")
+    x2, ldx = _rows_view(x, "x")
+    rows, c = x2.shape
+    out = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
+    rc = _run("layer_norm", 0.0, 2.0 * rows * c + 8.0 * rows,
+              lambda: _l.load().vgen_row_stats(_p(x2), rows, c, ldx, float(eps), _p(out), _stream()), tag=f"stats rows{rows} c{c}")
+    _l.check(rc, "vgen_row_stats")
+    return out
+
+
+def fold_layer_norm(w, bias, gamma, beta):
+    """Fold a LayerNorm's affine part into the linear that follows it (host-side, once per weight load).
+
+    w [n, k] / bias [n] or None (fp32 masters), gamma / beta [k].  Returns (w' fp16 [n, k] = w * gamma, col_sum fp32 [n] of the
+    ROUNDED w', bias' fp32 [n] = bias + w @ beta):  LN(x) w^T + bias = rstd (x w'^T) - mean rstd col_sum + bias'."""
+    w32, g, be = w.detach().float(), gamma.detach().float(), beta.detach().float()
+    wf = (w32 * g[None, :]).to(torch.float16)
+    lb = w32.double() @ be.double()
+    if bias is not None:
+        lb = lb + bias.detach().double()
+    return wf, wf.double().sum(1).float(), lb.float()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@ norm/softmax statistics, fp16 rounding where the reference materialises an fp16 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import arch, ops
@@ -57,6 +59,9 @@ class _UNetBase(SpecModule):
     cfg_batch = True  # samplers may evaluate the cond / uncond CFG branches as one batch-2b forward (diffusion.cfg_forward)
     WOIMG = False     # HiGen: temporal branches contribute 0 when a single frame is sampled
     SR600 = False     # SR600: (2,1)-padded downsampling, row-cropped upsampling, filtered skips
+    # nn.LayerNorm folded into the projection that follows it (vgen_epilogue.row_stats): the normalised tokens are never written.
+    # VGEN_LN_FOLD=0 keeps the separate LayerNorm kernel (A/B; read when the weights are packed).
+    FOLD_LN = os.environ.get("VGEN_LN_FOLD", "1") != "0"
 
     def __init__(self, config=None, in_dim=4, dim=512, y_dim=512, context_dim=512, hist_dim=156, dim_condition=4,
                  out_dim=6, num_tokens=4, dim_mult=[1, 2, 3, 4], num_heads=None, head_dim=64, num_res_blocks=3,
@@ -118,8 +123,14 @@ class _UNetBase(SpecModule):
             W[p + "w"] = _f16(w[:, :, :, 0, 0].permute(0, 2, 1).reshape(w.shape[0], -1), dev)
             W[p + "b"] = _f32(sd[p + "bias"], dev)
 
+        def fold(key, wmat, bias, nrm):
+            """LayerNorm `nrm` folded into the linear `key` that consumes it (ops.fold_layer_norm)."""
+            wf, cs, lb = ops.fold_layer_norm(wmat, bias, sd[nrm + "weight"], sd[nrm + "bias"])
+            W[key], W[key + ".cs"], W[key + ".lb"] = _f16(wf, dev), _f32(cs, dev), _f32(lb, dev)
+
         def block(p, cross, cross1=False):
             a1, a2 = p + "attn1.", p + "attn2."
+            ln_fold = self.FOLD_LN and not cross1
             if cross1:   # disable_self_attn=True: attn1 attends to the context as well (util.py:700-702)
                 W[a1 + "q"] = _f16(sd[a1 + "to_q.weight"], dev)
                 W[a1 + "kv"] = _f16(torch.cat([sd[a1 + "to_k.weight"], sd[a1 + "to_v.weight"]], 0), dev)
@@ -134,10 +145,22 @@ class _UNetBase(SpecModule):
             lin(a2 + "to_out.0.")
             for nm in ("norm1.", "norm2.", "norm3."):
                 norm(p + nm)
-            gw, gb = sd[p + "ff.net.0.proj.weight"], sd[p + "ff.net.0.proj.bias"]
+            gw, gb = sd[p + "ff.net.0.proj.weight"].detach().float(), sd[p + "ff.net.0.proj.bias"].detach().float()
             bn = _geglu_bn(gw.shape[0])
-            wp, bp = ops.pack_geglu_weight(gw.detach().float(), gb.detach().float(), bn)
+            if ln_fold:
+                # norm1 -> attn1.qkv, norm2 -> attn2.q (cross) / attn2.qkv, norm3 -> GEGLU projection
+                fold(a1 + "qkv", torch.cat([sd[a1 + "to_q.weight"], sd[a1 + "to_k.weight"], sd[a1 + "to_v.weight"]], 0), None, p + "norm1.")
+                if cross:
+                    fold(a2 + "q", sd[a2 + "to_q.weight"], None, p + "norm2.")
+                else:
+                    fold(a2 + "qkv", torch.cat([sd[a2 + "to_q.weight"], sd[a2 + "to_k.weight"], sd[a2 + "to_v.weight"]], 0), None, p + "norm2.")
+                g3, b3 = sd[p + "norm3.weight"].detach().float(), sd[p + "norm3.bias"].detach().float()
+                gb = gb + gw @ b3
+                gw = gw * g3[None, :]
+            wp, bp = ops.pack_geglu_weight(gw, gb, bn)
             W[p + "ff.geglu.w"], W[p + "ff.geglu.b"], W[p + "ff.geglu.bn"] = _f16(wp, dev), _f32(bp, dev), bn
+            if ln_fold:
+                W[p + "ff.geglu.cs"] = _f32(W[p + "ff.geglu.w"].double().sum(1), dev)
             lin(p + "ff.net.2.")
 
         def layer(L):
@@ -240,18 +263,24 @@ class _UNetBase(SpecModule):
                            residual=hcur.view(b, f, h * w, L.cout) if last else None).view(hcur.shape)
         return t
 
-    def _self_attn_spatial(self, xn, W, p, heads, n, hw, inner):
-        qkv = ops.linear(xn, W[p + "qkv"])                      # [M, 3*inner]
+    @staticmethod
+    def _ln_linear(t, W, key, nrm):
+        """nn.LayerNorm `nrm` followed by the bias-free projection `key` (util.py:694-704): when the pack folded the norm into
+        the weights (key.cs present) only the row statistics are computed and the GEMM epilogue applies them."""
+        if key + ".cs" in W:
+            return ops.linear(t, W[key], bias=W[key + ".lb"], ln=(ops.row_stats(t), W[key + ".cs"]))
+        return ops.linear(ops.layer_norm(t, W[nrm + "g"], W[nrm + "b"]), W[key])
+
+    def _self_attn_spatial(self, t, W, p, nrm, heads, n, hw, inner):
+        qkv = self._ln_linear(t, W, p + "qkv", nrm)             # [M, 3*inner]
         v3 = qkv.view(n, hw, 3 * inner)
         return ops.attention_d64(v3[:, :, :inner], v3[:, :, inner:2 * inner], v3[:, :, 2 * inner:], heads)
 
     def _basic_block_spatial(self, t, ctx_tokens, W, p, heads, n, hw, inner, f):
         """BasicTransformerBlock on tokens t [M, inner] (M = n*hw); ctx_tokens [b, L, ctx_dim] fp16."""
-        xn = ops.layer_norm(t, W[p + "norm1.g"], W[p + "norm1.b"])
-        a = self._self_attn_spatial(xn, W, p + "attn1.", heads, n, hw, inner)
+        a = self._self_attn_spatial(t, W, p + "attn1.", p + "norm1.", heads, n, hw, inner)
         t = ops.linear(a.view(-1, inner), W[p + "attn1.to_out.0.w"], bias=W[p + "attn1.to_out.0.b"], residual=t)
-        xn = ops.layer_norm(t, W[p + "norm2.g"], W[p + "norm2.b"])
-        q = ops.linear(xn, W[p + "attn2.q"]).view(n, hw, inner)
+        q = self._ln_linear(t, W, p + "attn2.q", p + "norm2.").view(n, hw, inner)
         bctx, lctx, cdim = ctx_tokens.shape
         kv = ops.linear(ctx_tokens.view(-1, cdim), W[p + "attn2.kv"]).view(bctx, lctx, 2 * inner)
         a = ops.attention_d64(q, kv[:, :, :inner], kv[:, :, inner:], heads, kv_batch_div=f)
@@ -259,8 +288,12 @@ class _UNetBase(SpecModule):
         return self._feed_forward(t, W, p)
 
     def _feed_forward(self, t, W, p):
-        xn = ops.layer_norm(t, W[p + "norm3.g"], W[p + "norm3.b"])
-        gg = ops.linear(xn, W[p + "ff.geglu.w"], bias=W[p + "ff.geglu.b"], geglu=True, bn=W[p + "ff.geglu.bn"])
+        if p + "ff.geglu.cs" in W:   # norm3 folded into the GEGLU projection
+            gg = ops.linear(t, W[p + "ff.geglu.w"], bias=W[p + "ff.geglu.b"], geglu=True, bn=W[p + "ff.geglu.bn"],
+                            ln=(ops.row_stats(t), W[p + "ff.geglu.cs"]))
+        else:
+            xn = ops.layer_norm(t, W[p + "norm3.g"], W[p + "norm3.b"])
+            gg = ops.linear(xn, W[p + "ff.geglu.w"], bias=W[p + "ff.geglu.b"], geglu=True, bn=W[p + "ff.geglu.bn"])
         return ops.linear(gg, W[p + "ff.net.2.w"], bias=W[p + "ff.net.2.b"], residual=t)
 
     def _spatial_transformer(self, x, ctx_tokens, L, W, f):
@@ -273,8 +306,8 @@ class _UNetBase(SpecModule):
         out = ops.linear(t, W[p + "proj_out.w"], bias=W[p + "proj_out.b"], residual=x.view(-1, c))
         return out.view(n, h, w, c)
 
-    def _temporal_attn(self, xn, W, p, heads, b, f, hw, inner):
-        qkv = ops.linear(xn, W[p + "qkv"]).view(b, f, hw, 3 * inner)
+    def _temporal_attn(self, t, W, p, nrm, heads, b, f, hw, inner):
+        qkv = self._ln_linear(t, W, p + "qkv", nrm).view(b, f, hw, 3 * inner)
         # all videos of the batch in one launch
         return ops.attention_temporal(qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:], heads, 64)
 
@@ -290,8 +323,7 @@ class _UNetBase(SpecModule):
         t = ops.linear(g.view(-1, c), W[p + "proj_in.w"], bias=W[p + "proj_in.b"])
         q = p + "transformer_blocks.0."
         for att, nrm in (("attn1.", "norm1."), ("attn2.", "norm2.")):
-            xn = ops.layer_norm(t, W[q + nrm + "g"], W[q + nrm + "b"])
-            a = self._temporal_attn(xn, W, q + att, L.heads, b, f, hw, inner)
+            a = self._temporal_attn(t, W, q + att, q + nrm, L.heads, b, f, hw, inner)
             t = ops.linear(a.view(-1, inner), W[q + att + "to_out.0.w"], bias=W[q + att + "to_out.0.b"], residual=t)
         t = self._feed_forward(t, W, q)
         out = ops.linear(t, W[p + "proj_out.w"], bias=W[p + "proj_out.b"], residual=x.view(-1, c))
