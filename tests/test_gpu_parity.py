@@ -72,6 +72,26 @@ def test_forward_parity(golden_dir, name):
     assert e_mine < 1.25 * e_ref16 + 2e-4
 
 
+@pytest.mark.parametrize("name", ["i2vgen_tiny", "higen_tiny"])
+def test_forward_parity_with_layer_norm_fold(golden_dir, name):
+    """The opt-in LayerNorm fold (UNet FOLD_LN: vgen_row_stats + the GEMM epilogue's row_stats / col_sum) against the same
+    reference golden and the same gate as the default path."""
+    case, m, inp, sdg, gold = _setup(golden_dir, name)
+    with torch.no_grad():
+        base = product_call(case, m, inp)
+        m.FOLD_LN = True
+        m.invalidate_packed()
+        mine = product_call(case, m, inp)
+        assert any(k.endswith(".cs") for k in m._packed), "the fold must have been packed"
+        with torch.autocast("cuda", dtype=torch.float16):
+            o16 = oracle_call(case, sdg, inp)
+    truth = torch.from_numpy(gold["out"]).cuda()
+    e_mine, e_base, e_ref16 = _rel_l2(mine, truth), _rel_l2(base, truth), _rel_l2(o16, truth)
+    print(f"{name} LN fold: {e_mine:.3e} (separate LayerNorm {e_base:.3e}, reference-autocast {e_ref16:.3e})")
+    assert not torch.equal(mine, base), "the folded path must actually have run"
+    assert e_mine < 5e-3 and e_mine < 1.25 * e_ref16 + 2e-4
+
+
 @pytest.mark.parametrize("name", ["t2v_tiny", "i2vgen_tiny"])
 def test_ddim_loop_parity(golden_dir, name):
     case, m, inp, sdg, gold = _setup(golden_dir, name)

@@ -24,21 +24,16 @@ def call(q, k, v, out, h, div, timing=None):
 
 
 # (VGEN_ATTN_TILES token, VGEN_ATTN_STAGGER) variants of vgen_attention_d64 to compare; --variants a,b,c selects tokens
-VARIANTS = [("2", None), ("3", None), ("t1", None), ("t1L", None), ("t1x4", None), ("t1x8", None), ("t2", None), ("t2x4", None), ("t2x8", None)]
+VARIANTS = [("auto", None), ("2", None), ("3", None), ("t1", None), ("t2", None)]
 
 
 def set_variant(tok):
-    """token = VGEN_ATTN_TILES value, optionally suffixed with 'n' (VGEN_ATTN_NOPWAIT=1, SS-form kernels) or 'L'
-    (VGEN_ATTN_EARLYLD=0, TS family); 'auto' = the library's shape heuristic"""
+    """token = VGEN_ATTN_TILES value ('2', '3', 't1', 't2'), or 'auto' = the library's shape heuristic"""
     tok = str(tok)
-    nop = tok in ("2n", "3n")
-    late = tok.endswith("L")
-    os.environ["VGEN_ATTN_NOPWAIT"] = "1" if nop else "0"
-    os.environ["VGEN_ATTN_EARLYLD"] = "0" if late else "1"
     if tok == "auto":
         os.environ.pop("VGEN_ATTN_TILES", None)
     else:
-        os.environ["VGEN_ATTN_TILES"] = tok[:-1] if (nop or late) else tok
+        os.environ["VGEN_ATTN_TILES"] = tok
 
 
 def sdpa_check(tokens):
@@ -127,8 +122,6 @@ def main():
             res.append(row)
     os.environ.pop("VGEN_ATTN_TILES", None)
     os.environ.pop("VGEN_ATTN_STAGGER", None)
-    os.environ.pop("VGEN_ATTN_NOPWAIT", None)
-    os.environ.pop("VGEN_ATTN_EARLYLD", None)
     from vgen_b200 import ops
     for (b, l) in ([(2, 14080), (4, 14400), (2, 1792)] if only in (None, "d512") else []):
         qkv = torch.randn(b, l, 1536, generator=g).half().cuda()

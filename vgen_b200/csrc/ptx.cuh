@@ -365,23 +365,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// three-input maximum (FMNMX3) and packed two-lane fp32 FMA (FFMA2) of sm_100: half the issue slots of their scalar forms
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-// {a.x * s.x + m.x, a.y * s.y + m.y}, each lane rounded like fmaf
-__device__ __forceinline__ float2 fma2(float ax, float ay, float2 s, float2 m) {
-  unsigned long long ra, rs, rm, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rs) : "f"(s.x), "f"(s.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rm) : "f"(m.x), "f"(m.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rs), "l"(rm));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -59,9 +59,12 @@ class _UNetBase(SpecModule):
     cfg_batch = True  # samplers may evaluate the cond / uncond CFG branches as one batch-2b forward (diffusion.cfg_forward)
     WOIMG = False     # HiGen: temporal branches contribute 0 when a single frame is sampled
     SR600 = False     # SR600: (2,1)-padded downsampling, row-cropped upsampling, filtered skips
-    # nn.LayerNorm folded into the projection that follows it (vgen_epilogue.row_stats): the normalised tokens are never written.
-    # VGEN_LN_FOLD=0 keeps the separate LayerNorm kernel (A/B; read when the weights are packed).
-    FOLD_LN = os.environ.get("VGEN_LN_FOLD", "1") != "0"
+    # nn.LayerNorm folded into the projection that follows it (vgen_row_stats + vgen_epilogue.row_stats / col_sum: the normalised
+    # tokens are never written).  OFF by default: on config 2 it halves the LayerNorm family (8.5 -> 4.3 ms / step) but the k = 320
+    # projections that consume it are epilogue-bound and pay for the extra per-column terms (+6.3 ms), a wash within run-to-run
+    # noise (profiles/r02r_bench_i2vgen_lnfold{0,1}.json).  VGEN_LN_FOLD=1, or FOLD_LN = True on a module followed by
+    # invalidate_packed(), turns it on; parity is the same (tests/test_gpu_parity.py).
+    FOLD_LN = os.environ.get("VGEN_LN_FOLD", "0") == "1"
 
     def __init__(self, config=None, in_dim=4, dim=512, y_dim=512, context_dim=512, hist_dim=156, dim_condition=4,
                  out_dim=6, num_tokens=4, dim_mult=[1, 2, 3, 4], num_heads=None, head_dim=64, num_res_blocks=3,
