@@ -289,6 +289,8 @@ def group_attention():
                                                (2, 1, 384, 65, 2, False)]:
             if stagger == 0 and lq > 1000:
                 continue
+            if os.environ.get("VGEN_CHECK_SMALL") == "1" and lq * lk > 4_000_000:
+                continue      # compute-sanitizer passes (tools/r02s_gpu.sh): the big launches take minutes under racecheck
 
             def f():
                 inner = heads * 64
