@@ -28,7 +28,7 @@ VARIANTS = [("auto", None), ("2", None), ("3", None), ("t1", None), ("t2", None)
 
 
 def set_variant(tok):
-    """token = VGEN_ATTN_TILES value ('2', '3', 't1', 't2'), or 'auto' = the library's shape heuristic"""
+    """token = VGEN_ATTN_TILES value ('2', '3', 't1', 't2', 't3'), or 'auto' = the library's shape heuristic"""
     tok = str(tok)
     if tok == "auto":
         os.environ.pop("VGEN_ATTN_TILES", None)
@@ -74,7 +74,7 @@ def main():
     shapes = [(32, 5, 14080, 14080, 1), (32, 10, 3520, 3520, 1), (32, 20, 880, 880, 1), (32, 20, 220, 220, 1),
               (32, 5, 14080, 145, 16), (32, 10, 3520, 145, 16)]
     if only is not None:
-        shapes = [] if only == "d512" else [shapes[int(only)]]
+        shapes = [] if only == "d512" else [shapes[int(x)] for x in only.split(",")]
     for (b, h, lq, lk, div) in shapes:
         inner = h * 64
         if lq == lk and div == 1:

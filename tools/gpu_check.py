@@ -280,8 +280,8 @@ def group_attention():
 
     # the library's shape heuristic first, then every instantiation of the tcgen05 kernel forced (VGEN_ATTN_TILES: SS form with
     # 2 q-tiles x 128-key blocks or 3 q-tiles x 64-key blocks -- also without its start-up stagger --, and the TS family with P
-    # in tensor memory, one or two q-tiles per CTA)
-    for (tiles, stagger) in [(None, None), ("2", None), ("3", None), ("3", 0), ("t1", None), ("t2", None)]:
+    # in tensor memory: one or two q-tiles per CTA, and the one-score-buffer form that fits three CTAs per SM)
+    for (tiles, stagger) in [(None, None), ("2", None), ("3", None), ("3", 0), ("t1", None), ("t2", None), ("t3", None)]:
         for (b, heads, lq, lk, div, fused) in [(1, 1, 128, 128, 1, False), (1, 1, 256, 128, 1, False), (1, 1, 256, 256, 1, False),
                                                (2, 2, 300, 300, 1, True), (2, 5, 880, 880, 1, True), (4, 5, 220, 77, 4, False),
                                                (4, 10, 3520, 145, 2, False), (1, 5, 14080, 14080, 1, True), (3, 1, 96, 96, 1, True),

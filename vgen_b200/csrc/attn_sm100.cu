@@ -436,45 +436,55 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
 // the early load only delays the P store queued behind it); FFMA2 for the scale-and-subtract, FMNMX3 for the row maximum, one
 // register set and the next block's load queued before the store wait (10.48 -> 10.99 / 9.83 -> 13.06 ms); every 4th / 8th
 // exponential as a Cody-Waite + degree-3 polynomial on the FMA pipe (11.2 / 11.5 ms and 11.7 / 12.0 ms on that base).
-template <int kNT_>
+template <int kNT_, int kSBufs_ = 2, bool kTcSum_ = true, int kCtasPerSm_ = (kNT_ == 1 ? 2 : 1)>
 struct AttnTsCfg {
   static constexpr int kNT = kNT_;
+  static constexpr int kSBufs = kSBufs_;                // score buffers per tile (2: QK runs two blocks ahead; 1: one)
+  static constexpr bool kTcSum = kTcSum_;               // row sums on the tensor core (16 more O columns) or in the softmax warps
   static constexpr int kTileK = 64;
   static constexpr int kThreads = 32 * (5 * kNT + 1);
   static constexpr int kKBytes = kTileK * kD * 2;       // 8 KB
-  static constexpr int kStageLog2 = 2, kKvStages = 4;
-  static constexpr int kNumBars = 1 + 4 * kKvStages + 6 * kNT;
-  static constexpr int kDataBytes = kNT * kQBytes + 2 * kKvStages * kKBytes + 2048;   // Q, K ring, V ring, ones atom
-  static constexpr uint32_t kTmemCols = kNT == 1 ? 256 : 512;
-  static constexpr int kCtasPerSm = kNT == 1 ? 2 : 1;
-  static_assert(kNT * 208 <= (int)kTmemCols, "TMEM columns");
+  static constexpr int kStageLog2 = kSBufs == 2 ? 2 : 1, kKvStages = 1 << kStageLog2;
+  static constexpr int kNumBars = 1 + 4 * kKvStages + 3 * kSBufs * kNT;
+  static constexpr int kDataBytes = kNT * kQBytes + 2 * kKvStages * kKBytes + (kTcSum ? 2048 : 0);   // Q, K ring, V ring, ones atom
+  static constexpr int kTmemNeed = kNT * (64 * kSBufs + (kTcSum ? 80 : 64));
+  static constexpr uint32_t kTmemCols = kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
+  static constexpr int kCtasPerSm = kCtasPerSm_;
+  static_assert(kTmemNeed <= 512 && kCtasPerSm * (int)kTmemCols <= 512, "TMEM columns");
   static constexpr size_t smem_bytes() { return (size_t)kDataBytes + kNumBars * 8 + 16 + 1024; }
+  static_assert(kCtasPerSm * (kDataBytes + kNumBars * 8 + 16 + 1024 + 1024) <= 227 * 1024, "shared memory of the co-resident CTAs");
 };
 
 template <class Cfg, bool kTiming>
 __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
   constexpr int kNT = Cfg::kNT, kTileK = Cfg::kTileK, kKBytes = Cfg::kKBytes;
   constexpr int kKvStages = Cfg::kKvStages, kStageLog2 = Cfg::kStageLog2;
-  constexpr int kOCols = 80;
-  constexpr int kOBase = 128 * kNT;
+  constexpr int kSBufs = Cfg::kSBufs;
+  constexpr bool kTcSum = Cfg::kTcSum;
+  constexpr int kOCols = kTcSum ? 80 : 64;
+  constexpr int kTileCols = 64 * kSBufs;          // S / P columns of one q-tile
+  constexpr int kOBase = kTileCols * kNT;
+  // block j lives in score buffer sbuf(j); it is the (j / kSBufs)-th use of that buffer's barriers
+  auto sbuf = [](int j) { return kSBufs == 2 ? (j & 1) : 0; };
+  auto sphase = [](int j) { return (uint32_t)((kSBufs == 2 ? (j >> 1) : j) & 1); };
   constexpr int kProducerWarp = 4 * kNT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // kNT x 16 KB
   uint8_t* sK = sQ + kNT * kQBytes;                    // ring of K blocks
   uint8_t* sV = sK + kKvStages * kKBytes;              // ring of V blocks
-  uint8_t* sOnes = sV + kKvStages * kKBytes;           // 2 KB constant MN-major atom (16 keys x 64 columns, column 0 = 1)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 2048);
+  uint8_t* sOnes = sV + kKvStages * kKBytes;           // kTcSum: 2 KB constant MN-major atom (16 keys x 64 columns, column 0 = 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (kTcSum ? 2048 : 0));
   uint64_t* q_full = bars;                        // [1]
   uint64_t* k_full = q_full + 1;                  // [stages]
   uint64_t* k_empty = k_full + kKvStages;         // [stages] every tile's QK(j) finished
   uint64_t* v_full = k_empty + kKvStages;         // [stages]
   uint64_t* v_empty = v_full + kKvStages;         // [stages] every tile's PV(j) finished
-  uint64_t* s_full = v_empty + kKvStages;         // [kNT][2] per q-tile and S buffer: S(j) written by QK(j)
-  uint64_t* p_full = s_full + 2 * kNT;            // [kNT][2] per q-tile and S buffer: P(j) stored over S(j), O rescaled
-  uint64_t* o_full = p_full + 2 * kNT;            // [kNT][2] per q-tile and S buffer: PV(j) finished (O readable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2 * kNT);
-  static_assert(1 + 4 * Cfg::kKvStages + 6 * Cfg::kNT == Cfg::kNumBars, "barrier count");
+  uint64_t* s_full = v_empty + kKvStages;         // [kNT][kSBufs] per q-tile and S buffer: S(j) written by QK(j)
+  uint64_t* p_full = s_full + kSBufs * kNT;       // [kNT][kSBufs] per q-tile and S buffer: P(j) stored over S(j), O rescaled
+  uint64_t* o_full = p_full + kSBufs * kNT;       // [kNT][kSBufs] per q-tile and S buffer: PV(j) finished (O readable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + kSBufs * kNT);
+  static_assert(1 + 4 * Cfg::kKvStages + 3 * Cfg::kSBufs * Cfg::kNT == Cfg::kNumBars, "barrier count");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
@@ -492,7 +502,7 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], kNT);
     }
-    for (int i = 0; i < 2 * kNT; ++i) {
+    for (int i = 0; i < kSBufs * kNT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
@@ -503,7 +513,7 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tmem_relinquish();
   }
-  if (warp < 4) {
+  if (kTcSum && warp < 4) {
     // rows = keys (two 8-row groups 1024 B apart, like the V tile), 128 B per row, 128B-swizzled: the 16-byte piece holding
     // column 0 of row r sits at piece index (0 ^ (r & 7))
     const int t = threadIdx.x;                       // 128 threads x 16 B = 2 KB
@@ -544,14 +554,14 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
     }
   } else if (warp > kProducerWarp) {
     // ------------------------------------------------------------------ MMA issue for q-tile i (warp-uniform loop)
-    // QK(0) QK(1) { PV(j) QK(j+2) } ...: the tensor pipe executes one thread's MMAs in issue order, so QK(j+2) overwrites the
-    // S buffer only after PV(j) has read P(j) out of it.
+    // QK(0) [QK(1)] { PV(j) QK(j + kSBufs) } ...: the tensor pipe executes one thread's MMAs in issue order, so QK(j + kSBufs)
+    // overwrites the S buffer only after PV(j) has read P(j) out of it.
     const int i = warp - kProducerWarp - 1;
     const uint32_t idesc_qk = umma_idesc_f16(kTileQ, kTileK, 0, 0);
     const uint32_t idesc_pv = umma_idesc_f16(kTileQ, kOCols, 0, 1);  // A = P (TMEM, K-major), B = V + the ones atom (MN-major)
     const uint32_t ones_addr = smem_u32(sOnes);
     const uint32_t q_addr = smem_u32(sQ) + i * kQBytes, k_addr = smem_u32(sK), v_addr0 = smem_u32(sV);
-    const uint32_t t_s = tmem + 128 * i, t_o = tmem + kOBase + i * kOCols;
+    const uint32_t t_s = tmem + kTileCols * i, t_o = tmem + kOBase + i * kOCols;
     auto issue_qk = [&](int j) {
       const int st = j & (kKvStages - 1);
       mbar_wait(&k_full[st], (j >> kStageLog2) & 1, 32);
@@ -560,36 +570,36 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
         const uint64_t a_desc = umma_desc_sw128(q_addr, 16, 1024);
         const uint64_t b_desc = umma_desc_sw128(k_addr + st * kKBytes, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s + 64 * (j & 1), a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[2 * i + (j & 1)]);
+        for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s + 64 * sbuf(j), a_desc + 2 * k, b_desc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[kSBufs * i + sbuf(j)]);
         umma_commit(&k_empty[st]);  // this tile is done with K(j); the slot frees when every tile is
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0, 33);
     issue_qk(0);
-    if (nkv > 1) issue_qk(1);
+    if (kSBufs == 2 && nkv > 1) issue_qk(1);
     for (int j = 0; j < nkv; ++j) {
       const int st = j & (kKvStages - 1);
-      mbar_wait(&p_full[2 * i + (j & 1)], (j >> 1) & 1, 34);
+      mbar_wait(&p_full[kSBufs * i + sbuf(j)], sphase(j), 34);
       mbar_wait(&v_full[st], (j >> kStageLog2) & 1, 35);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t v_addr = v_addr0 + st * kKBytes;
-        const uint32_t a_tmem = t_s + 64 * (j & 1);      // P(j): 64 keys = 32 columns of packed fp16 pairs
+        const uint32_t a_tmem = t_s + 64 * sbuf(j);      // P(j): 64 keys = 32 columns of packed fp16 pairs
 #pragma unroll
         for (int ks = 0; ks < kTileK / 16; ++ks) {
           // B: V rows [16*ks, 16*ks+16) (K dimension), 64 contiguous d (MN-major), 8-row groups 1024 B apart; the second
           // 64-column atom of B is the ones tile (leading byte offset = its distance from this K step)
           const uint32_t vk = v_addr + ks * 16 * 128;
-          const uint64_t b_desc = umma_desc_sw128(vk, ones_addr - vk, 1024);
+          const uint64_t b_desc = umma_desc_sw128(vk, kTcSum ? ones_addr - vk : 1024u, 1024);
           umma_f16_ts(t_o, a_tmem + 8 * ks, b_desc, idesc_pv, (j | ks) != 0);  // O accumulates over blocks
         }
-        umma_commit(&o_full[2 * i + (j & 1)]);
+        umma_commit(&o_full[kSBufs * i + sbuf(j)]);
         umma_commit(&v_empty[st]);
       }
       __syncwarp();
-      if (j + 2 < nkv) issue_qk(j + 2);
+      if (j + kSBufs < nkv) issue_qk(j + kSBufs);
     }
   } else {
     // ---------------------------------------------------------------- softmax / output warps
@@ -597,11 +607,12 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
     const int q = warp & 3;           // TMEM lane quadrant
     const int r = q * 32 + lane;      // row within the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t t_s = tmem + 128 * i + lane_base;
+    const uint32_t t_s = tmem + kTileCols * i + lane_base;
     const uint32_t t_o = tmem + kOBase + i * kOCols + lane_base;
     const float sl2 = p.scale_log2;
 
     float m_ref = -INFINITY;  // reference max (raw score units) all of this row's exponentials are relative to
+    float l_run = 0.f;        // !kTcSum: the row sum
     long long tm_wait_s = 0, tm_ldmax = 0, tm_exp = 0, tm_c0 = 0, tm_c1 = 0, tm_start = 0;
     if (kTiming) tm_start = clock64();
 
@@ -617,21 +628,27 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
       }
     };
     auto wait_and_load = [&](uint32_t (&s)[2][32], int j) {   // tcgen05.ld of S(j) issued, NOT waited for
-      mbar_wait(&s_full[2 * i + (j & 1)], (j >> 1) & 1, 40);
+      mbar_wait(&s_full[kSBufs * i + sbuf(j)], sphase(j), 40);
       tc_fence_after();
-      tmem_ld32(t_s + 64 * (j & 1), s[0]);
-      tmem_ld32(t_s + 64 * (j & 1) + 32, s[1]);
+      tmem_ld32(t_s + 64 * sbuf(j), s[0]);
+      tmem_ld32(t_s + 64 * sbuf(j) + 32, s[1]);
     };
     // exponentials of 32 scores -> 16 packed fp16 pairs -> TMEM columns [16 c, 16 c + 16) of the block's S buffer
     auto exp_store = [&](const uint32_t (&sc)[32], int c, float neg_ms, uint32_t t_p) {
       uint32_t pk[16];
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
         const float e0 = fast_exp2(fmaf(__uint_as_float(sc[2 * t]), sl2, neg_ms));
         const float e1 = fast_exp2(fmaf(__uint_as_float(sc[2 * t + 1]), sl2, neg_ms));
+        if (!kTcSum) {
+          l0 += e0;
+          l1 += e1;
+        }
         pk[t] = pack_half2(e0, e1);
       }
       tmem_st16(t_p + 16 * c, pk);
+      if (!kTcSum) l_run += l0 + l1;
     };
     // One key block whose scores are in `cur` (loaded and waited for); the next block's scores are loaded into `nxt` at the end.
     auto step = [&](uint32_t (&cur)[2][32], uint32_t (&nxt)[2][32], int j) {
@@ -653,11 +670,11 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
         if (j > 0) {
           const float alpha = fast_exp2((m_ref - m_new) * sl2);  // 1 for rows that do not advance
           // O must be complete up to PV(j-1) before it is touched
-          mbar_wait(&o_full[2 * i + ((j - 1) & 1)], ((j - 1) >> 1) & 1, 41);
+          mbar_wait(&o_full[kSBufs * i + sbuf(j - 1)], sphase(j - 1), 41);
           tc_fence_after();
           uint32_t o[16];
 #pragma unroll 1
-          for (int c = 0; c < kOCols; c += 16) {   // 64 output columns + the row-sum column and its 15 zero companions
+          for (int c = 0; c < kOCols; c += 16) {   // 64 output columns (+ kTcSum: the row-sum column and its 15 zero companions)
             tmem_ld16(t_o + c, o);
             tmem_ld_wait();
 #pragma unroll
@@ -665,19 +682,20 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
             tmem_st16(t_o + c, o);
           }
           tmem_st_wait();
+          l_run *= alpha;
         }
         m_ref = m_new;
       }
       if (kTiming) { tm_c0 = clock64(); tm_ldmax += tm_c0 - tm_c1; }
       const float neg_ms = -m_ref * sl2;
-      const uint32_t t_p = t_s + 64 * (j & 1);
+      const uint32_t t_p = t_s + 64 * sbuf(j);
       exp_store(cur[0], 0, neg_ms, t_p);
       exp_store(cur[1], 1, neg_ms, t_p);
       // P(j) stored (and O rescaled): publish to the MMA warp
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[2 * i + (j & 1)]);
+      if (lane == 0) mbar_arrive(&p_full[kSBufs * i + sbuf(j)]);
       if (kTiming) { tm_c1 = clock64(); tm_exp += tm_c1 - tm_c0; }
       if (j + 1 < nkv) {
         wait_and_load(nxt, j + 1);
@@ -688,30 +706,36 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
       if (kTiming) { tm_c0 = clock64(); tm_wait_s += tm_c0 - tm_c1; }
     };
 
-    uint32_t sa[2][32], sb[2][32];   // alternating score register sets
+    uint32_t sa[2][32];
     wait_and_load(sa, 0);
     tmem_ld_wait();
     reg_pin32(sa[0]);
     reg_pin32(sa[1]);
-    for (int j = 0; j < nkv; j += 2) {
-      step(sa, sb, j);
-      if (j + 1 < nkv) step(sb, sa, j + 1);
+    if constexpr (Cfg::kCtasPerSm >= 3) {
+      // <= 96 registers per thread: one score register set (a block's scores are dead once its exponentials are packed)
+      for (int j = 0; j < nkv; ++j) step(sa, sa, j);
+    } else {
+      uint32_t sb[2][32];   // alternating score register sets (measured faster than one set: 10.48 vs 10.99 ms, TS1 at 14080^2)
+      for (int j = 0; j < nkv; j += 2) {
+        step(sa, sb, j);
+        if (j + 1 < nkv) step(sb, sa, j + 1);
+      }
     }
     if (kTiming && p.timing && i < 2 && q == 0 && lane == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
       long long* t = p.timing + (kNT == 1 ? 0 : i) * 8;
       t[0] = tm_wait_s, t[1] = tm_ldmax, t[2] = 0, t[3] = tm_exp, t[4] = clock64() - tm_start, t[5] = nkv;
     }
     // ---- output: O / l  (l = the row-sum column, accumulated by the tensor core)
-    mbar_wait(&o_full[2 * i + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1, 42);
+    mbar_wait(&o_full[kSBufs * i + sbuf(nkv - 1)], sphase(nkv - 1), 42);
     tc_fence_after();
     const int row = q0 + i * kTileQ + r;
     uint32_t o16[16];
-    tmem_ld16(t_o + kD, o16);
+    if (kTcSum) tmem_ld16(t_o + kD, o16);
     uint32_t oa[32], ob[32];
     tmem_ld32(t_o + 0, oa);
     tmem_ld32(t_o + 32, ob);
     tmem_ld_wait();
-    const float inv_l = 1.0f / __uint_as_float(o16[0]);
+    const float inv_l = 1.0f / (kTcSum ? __uint_as_float(o16[0]) : l_run);
     __half* orow = p.out + (long)batch * p.out_batch_stride + (long)row * p.ldo + head * kD;
     if (row < p.lq) {
 #define VG_ATTN_STORE(ARR, C0)                                                                                  \
@@ -739,14 +763,19 @@ __device__ __forceinline__ void attn_sm100_ts_body(const AttnParams& p) {
 
 using AttnTs1 = AttnTsCfg<1>;
 using AttnTs2 = AttnTsCfg<2>;
+// one score buffer, row sums in the softmax warps: 128 TMEM columns and 49 KB of shared memory per CTA, THREE CTAs per SM
+// (three softmax warps per sub-partition without doubling the per-key barrier traffic)
+using AttnTs3 = AttnTsCfg<1, 1, false, 3>;
 #define VG_ATTN_TS_KERNEL(NAME, CFG, TIMING)                                                                 \
   __global__ void __launch_bounds__(CFG::kThreads, CFG::kCtasPerSm) NAME(const __grid_constant__ AttnParams p) { \
     attn_sm100_ts_body<CFG, TIMING>(p);                                                                      \
   }
 VG_ATTN_TS_KERNEL(attn_sm100_ts1_kernel, AttnTs1, false)
 VG_ATTN_TS_KERNEL(attn_sm100_ts2_kernel, AttnTs2, false)
+VG_ATTN_TS_KERNEL(attn_sm100_ts3_kernel, AttnTs3, false)
 VG_ATTN_TS_KERNEL(attn_sm100_ts1_timing_kernel, AttnTs1, true)
 VG_ATTN_TS_KERNEL(attn_sm100_ts2_timing_kernel, AttnTs2, true)
+VG_ATTN_TS_KERNEL(attn_sm100_ts3_timing_kernel, AttnTs3, true)
 #undef VG_ATTN_TS_KERNEL
 
 using AttnCfg2 = AttnCfg<2, 128>;
@@ -812,7 +841,7 @@ static int attention_d64_impl(const void* q, const void* k, const void* v, void*
   {
     const char* e = getenv("VGEN_ATTN_TILES");
     tiles_mode = (e && e[0] == '3') ? 3 : (e && e[0] == '2') ? 2 : 0;
-    if (e && e[0] == 't' && (e[1] == '1' || e[1] == '2')) tiles_mode = 10 * (e[1] - '0');
+    if (e && e[0] == 't' && (e[1] == '1' || e[1] == '2' || e[1] == '3')) tiles_mode = 10 * (e[1] - '0');
     e = getenv("VGEN_ATTN_TCSUM");
     tcsum_mode = (e && e[0] == '0') ? 0 : 1;
     e = getenv("VGEN_ATTN_STAGGER");
@@ -866,6 +895,8 @@ static int attention_d64_impl(const void* q, const void* k, const void* v, void*
     VG_ATTN_TS_ATTR(attn_sm100_ts2_kernel, AttnTs2);
     VG_ATTN_TS_ATTR(attn_sm100_ts1_timing_kernel, AttnTs1);
     VG_ATTN_TS_ATTR(attn_sm100_ts2_timing_kernel, AttnTs2);
+    VG_ATTN_TS_ATTR(attn_sm100_ts3_kernel, AttnTs3);
+    VG_ATTN_TS_ATTR(attn_sm100_ts3_timing_kernel, AttnTs3);
 #undef VG_ATTN_TS_ATTR
     attr_once.mark();
   }
@@ -875,6 +906,10 @@ static int attention_d64_impl(const void* q, const void* k, const void* v, void*
       dim3 grid((unsigned)cdiv(lq, kTileQ), (unsigned)heads, (unsigned)batch);
       launch_kernel(timing ? attn_sm100_ts1_timing_kernel : attn_sm100_ts1_kernel, dim3(grid), dim3(AttnTs1::kThreads),
                     AttnTs1::smem_bytes(), st, p);
+    } else if (tiles / 10 == 3) {
+      dim3 grid((unsigned)cdiv(lq, kTileQ), (unsigned)heads, (unsigned)batch);
+      launch_kernel(timing ? attn_sm100_ts3_timing_kernel : attn_sm100_ts3_kernel, dim3(grid), dim3(AttnTs3::kThreads),
+                    AttnTs3::smem_bytes(), st, p);
     } else {
       dim3 grid((unsigned)cdiv(lq, 2 * kTileQ), (unsigned)heads, (unsigned)batch);
       launch_kernel(timing ? attn_sm100_ts2_timing_kernel : attn_sm100_ts2_kernel, dim3(grid), dim3(AttnTs2::kThreads),
