@@ -804,9 +804,9 @@ __global__ void __launch_bounds__(AttnCfg3::kThreads, 1) attn_sm100_x3_timing_ke
 
 using namespace vg;
 
-// Which instantiation serves a shape when VGEN_ATTN_TILES is not set (measured on B200: see DESIGN.md section 3).
 // Which instantiation serves a shape when VGEN_ATTN_TILES is not set (internal codes: 2 = SS <2 tiles, 128 keys>, 3 = SS <3, 64>,
-// 10 / 20 = TS with 1 / 2 tiles per CTA).  Measured on B200 (profiles/r02q_attn_*.log, ms):
+// 10 / 20 / 30 = TS1 / TS2 / TS3).  Measured on B200 (profiles/r02q_attn_*.log; TS3: r02t / r02u_attn_ts3.log: 11.32, 1.525, 0.246,
+// 0.0442, 0.334, 0.176 -- ahead only on the two cross-attention rows), ms:
 //   lq x lk        SS<2,128>  SS<3,64>   TS1      TS2
 //   14080 x 14080   9.70       9.79     10.48     9.83
 //    3520 x 3520    1.446      1.396     1.401    1.406
