@@ -7,12 +7,15 @@
 // (batch, head); fp16 inputs, fp32 scores / softmax / accumulation, P rounded to fp16 for the PV
 // product (what the CUTLASS/FA2 kernels behind xformers do).
 //
-// The body is a template on <kNT q-tiles per CTA, kTileK keys per block>; two instantiations are built:
-//   <2, 128>  256 query rows / CTA, 11 warps, 128-key blocks (168 registers / thread)
-//   <3, 64>   384 query rows / CTA, 16 warps, 64-key blocks (<= 128 registers / thread): THREE softmax warps per SM
-//             sub-partition, so that while one tile sits in its MUFU-free phase (barrier round trips, tcgen05.ld, row max:
-//             ~30 % of a tile's block time) the other two keep the sub-partition's MUFU pipe saturated -- two warps in
-//             lock step cannot (measured 24 % idle), and one warp alone does not reach the pipe's rate.
+// Two kernel families live in this file; vgen_attention_d64 picks by key length (attn_default_tiles, table at the launcher):
+//   SS family (first body): P goes through shared memory (SS-form tcgen05.mma).  Serves lk > 4096.
+//   TS family (second body, "TS" comment below): P stays in tensor memory (TS-form tcgen05.mma), small CTAs, 2-3 per SM.
+//
+// SS family.  The body is a template on <kNT q-tiles per CTA, kTileK keys per block>; two instantiations are built:
+//   <2, 128>  256 query rows / CTA, 11 warps, 128-key blocks (168 registers / thread): the default
+//   <3, 64>   384 query rows / CTA, 16 warps, 64-key blocks (118 registers / thread): three softmax warps per SM sub-partition.
+//             Built to test whether a third warp fills the MUFU pipe while the others sit in their MUFU-free phases; it does
+//             not (9.79 vs 9.70 ms on the 14080^2 launch: the doubled barrier traffic per key eats the gain) -- knob only.
 // One CTA = kNT 128-row tiles of one (batch, head), 5 kNT + 1 warps:
 //   warps 4i .. 4i+3   softmax + output for q-tile i (thread r <-> TMEM lane r)
 //   warp 4 kNT         TMA producer: Q once, then separate rings of K and V blocks of kTileK keys (K(j) is
@@ -429,7 +432,10 @@ __device__ __forceinline__ void attn_sm100_body(const AttnParams& p) {
 // S buffers need.  Per tile: S/P buffers [128 i, 128 i + 128), O (+ the row-sum column) [128 kNT + 80 i, +80).
 //   kNT = 2: one CTA per SM, 11 warps, K/V blocks shared by both tiles (416 TMEM columns)
 //   kNT = 1: TWO CTAs per SM (256 TMEM columns and 82 KB of shared memory each), 6 warps: the two tiles of an SM are
-//            independent CTAs whose prologues / epilogues overlap (the 145-key cross attention is all prologue)
+//            independent CTAs whose prologues / epilogues overlap (the 145-key cross attention is all prologue): the default
+//            for lk <= 4096
+//   kNT = 1, ONE score buffer, row sums in the softmax warps ("TS3"): 128 TMEM columns, 49 KB, 96 registers: THREE CTAs per SM;
+//            QK(j+1) then has to wait for PV(j), which costs the tile ~990 cycles per block -- ahead only on the 145-key launches
 // Measured and rejected on top of this body (source: experiments/attn_ts_ffma2_fmnmx3_poly_earlyld.cu.txt; numbers for the 14080^2
 // launch, TS1 / TS2, profiles/r02q_attn_*.log vs r02r_attn_ts_microopt.log): issuing the tcgen05.ld of S(j+1) in the middle of block
 // j's exponentials into a second register set (10.48 -> 10.70 / 9.83 -> 10.38 ms: a warp's TMEM operations complete in order, so
